@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the effects-chain hot path on B200.
+
+Metric (BASELINE.json): Msamples/s through a 256-channel x 131072-tap `fir_p` chain, 1 sample =
+one double of one channel-frame at the chain input; weak scaling (every GPU owns 256 channels,
+independent streams, no collective on the data path).  One "step" = one block of --block frames
+(default 4096) x 256 channels through the chain.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                         # the reference's CPU path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.  `value` = device-resident throughput (inputs in HBM, CUDA events
+on the launching stream); `e2e` = the same blocks through the C-ABI host call
+(dspb200_chain_run_host) from pinned host memory, copies inside the timed region; `roofline` =
+the partition-MAC kernel (k_fir_mac) against the measured HBM peak; `cpu_baseline` = the compiled
+reference (oracle/_ref) on this box's host cores over a bounded sample.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 48000
+CHANNELS_PER_GPU = 256
+TAPS = 131072
+METRIC = "Msamples/s through 256-ch 128k-tap fir_p chain"
+UNIT = "Msamples/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload definition: seeded decaying-noise IR per channel, noise-like input blocks
+# ------------------------------------------------------------------------------------------------
+def park_miller(seed, count):
+    """x -> 48271 x mod (2^31-1) (the reference's pm_rand1_r, util.h:127-148), vectorised."""
+    M = np.uint64(0x7fffffff)
+    pw = np.array([48271], dtype=np.uint64)
+    while pw.shape[0] < count:
+        pw = np.concatenate([pw, (pw * pw[-1]) % M])
+    return ((pw[:count] * np.uint64(seed)) % M).astype(np.float64)
+
+
+def make_ir(taps, channel):
+    u = 2.0 * park_miller(1 + channel, taps) / 2147483647.0 - 1.0
+    h = u * np.exp(-6.9 * np.arange(taps) / taps)
+    return h * (0.5 / np.sum(np.abs(h)))
+
+
+def make_irs(taps, channels, first_channel=0):
+    return np.stack([make_ir(taps, first_channel + c) for c in range(channels)], axis=1)
+
+
+def make_block(frames, channels, seed):
+    u = park_miller(1000 + seed, frames * channels) / 2147483647.0 - 0.5
+    return u.reshape(frames, channels)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs: the compiled reference on host cores (the only place oracle/ is executed here)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    ir_path, ch, block, warm, steps, seconds = args
+    sys.path.insert(0, ROOT)
+    from oracle import ref          # checker / baseline only
+    c = ref.RefChain("fir_p -t pcm -e double -c %d -r %d %s" % (ch, FS, ir_path), FS, ch)
+    c.run_inplace(block, refill=True)
+    for _ in range(warm):
+        c.run_inplace(block)
+    t0 = time.perf_counter()
+    n = 0
+    while (steps and n < steps) or (not steps and time.perf_counter() - t0 < seconds):
+        c.run_inplace(block)
+        n += 1
+    dt = time.perf_counter() - t0
+    c.close()
+    return n, dt
+
+
+def cpu_reference_run(block, warm, steps=0, seconds=10.0, ch_per_proc=2, procs=None):
+    """All host cores: `procs` processes, each a reference fir_p chain of `ch_per_proc` channels with its own
+    131072-tap IRs (channels are independent, so this is how the reference would use the box)."""
+    from oracle import ref
+    if not ref.available():
+        return None
+    procs = procs or os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="dspb200_bench_")
+    ir_path = os.path.join(tmp, "ir.f64")
+    make_irs(TAPS, ch_per_proc).astype("<f8").tofile(ir_path)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(ir_path, ch_per_proc, block, warm, steps, seconds)] * procs)
+    os.remove(ir_path)
+    os.rmdir(tmp)
+    # every process ran concurrently; job throughput = sum of per-process rates
+    rate = sum(n * block * ch_per_proc / dt for n, dt in res)
+    blocks = sum(n for n, _ in res)
+    wall = max(dt for _, dt in res)
+    return {"value": rate / 1e6, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": "%d processes x %d ch x %d-frame blocks, %d blocks total in %.1f s; FFT backend = oracle/fftw3_shim.c (FFTW3 absent)"
+                      % (procs, ch_per_proc, block, blocks, wall),
+            "ms_per_step": wall / max(1, max(n for n, _ in res)) * 1e3, "steps_done": max(n for n, _ in res),
+            "channels": procs * ch_per_proc}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--block", type=int, default=4096)
+    ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU, help="channels per GPU")
+    ap.add_argument("--taps", type=int, default=TAPS)
+    ap.add_argument("--shared-ir", action="store_true", help="one IR for all channels (-c 1) instead of one per channel")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-slabs", type=int, default=4)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warm = max(1, a.steps), max(3, a.warmup)
+    config = {"workload": "fir_p %d taps x %d ch per GPU, %s IR, %d-frame blocks, fs %d" %
+                          (a.taps, a.channels, "shared" if a.shared_ir else "per-channel", a.block, FS),
+              "block_frames": a.block, "channels_per_gpu": a.channels, "taps": a.taps,
+              "parallelism": "channel-sharded x%d, no collective" % max(world, 1)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(a.block, warm, steps=steps)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdspref.so not built (needs /root/reference at build time)"}))
+            return 0
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import dsp_b200
+    if dsp_b200.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    C, F = a.channels, a.block
+    irs = make_ir(a.taps, 0)[:, None] if a.shared_ir else make_irs(a.taps, C, first_channel=rank * C)
+    n_pool = 8
+    blocks = [make_block(F, C, rank * 100 + i) for i in range(n_pool)]
+
+    # ---------------- mode D: device-resident blocks, CUDA events on the launching stream ------------
+    chain = dsp_b200.Chain(FS, C, devices=[local_rank]).add_fir(irs, block_hint=F)
+    d_blocks = [torch.from_numpy(b).cuda() for b in blocks]
+    d_out = torch.empty((F, C), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for i in range(warm):
+        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dsp_b200.profile_read("fir_mac")
+    dsp_b200.profile_enable(True)
+    launches0 = dsp_b200.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
+    e1.record()
+    barrier()
+    launches = dsp_b200.kernel_launches() - launches0
+    dsp_b200.profile_enable(False)
+    clocks = sampler.stop()
+    ms = reduce_max(e0.elapsed_time(e1))
+    mac_ms, mac_n = dsp_b200.profile_read("fir_mac")
+    fwd_ms, fwd_n = dsp_b200.profile_read("fir_fwd")
+    inv_ms, inv_n = dsp_b200.profile_read("fir_inv")
+    total_samples = float(world) * C * F * steps
+    value = total_samples / (ms * 1e-3) / 1e6
+    checksum = float(d_out.abs().sum().item())
+
+    # roofline of the dominant kernel: algorithmic bytes of one k_fir_mac launch:
+    #   per selected channel and bin: P FDL rows + (per-channel IR) P filter rows read, 1 row written, 16 B each
+    P = (a.taps + F - 1) // F
+    h = 0 if a.shared_ir else 1
+    mac_bytes = C * F * 16.0 * (P * (1 + h) + 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = None
+    if mac_n > 0:
+        mac_avg_s = mac_ms / mac_n * 1e-3
+        ach = mac_bytes / mac_avg_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_fir_mac", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_launch": mac_bytes, "avg_launch_us": mac_avg_s * 1e6, "launches": mac_n,
+                    "share_of_step": mac_ms / ms if ms > 0 else None,
+                    "other_kernels_us": {"k_fir_fwd": fwd_ms / max(fwd_n, 1) * 1e3, "k_fir_inv": inv_ms / max(inv_n, 1) * 1e3}}
+    chain.close()
+    del chain
+
+    # ---------------- mode A (e2e): the C-ABI host call on pinned host blocks ------------------------
+    e2e = None
+    if not a.no_e2e:
+        ch2 = dsp_b200.Chain(FS, C, devices=[local_rank], slabs_per_device=a.e2e_slabs).add_fir(irs, block_hint=F)
+        pins = [dsp_b200.PinnedArray((F, C)) for _ in range(n_pool)]
+        for p, b in zip(pins, blocks):
+            p.array[:] = b
+        pout = dsp_b200.PinnedArray((F, C))
+        for i in range(warm):
+            ch2.run_raw(F, pins[i % n_pool].ptr, pout.ptr)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            ch2.run_raw(F, pins[i % n_pool].ptr, pout.ptr)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = reduce_max(dt)
+        e2e = {"value": total_samples / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": F * C * 8, "d2h_bytes_per_step": F * C * 8,
+               "ms_per_step": dt / steps * 1e3, "api": "dspb200_chain_run_host, pinned host buffers, %d channel slabs" % a.e2e_slabs,
+               "checksum": float(np.abs(pout.array).sum())}
+        ch2.close()
+
+    launches_total = int(reduce_sum(float(launches)))
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        r = cpu_reference_run(F, 2, seconds=a.cpu_seconds)
+        if r:
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        config["l2"] = "per-step working set %.2f GB of FDL+filter spectra streamed from HBM (> 126 MB L2); %d rotating input blocks" % (mac_bytes / 1e9, n_pool)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,105 @@
+// common.cuh -- shared plumbing for libdspb200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace dspb200 {
+
+// ---- error reporting (thread-local message behind dspb200_last_error()) ------------------
+void set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+const char *get_error();
+
+#define CUDA_TRY(expr, fail_action)                                                        \
+	do {                                                                                   \
+		cudaError_t err__ = (expr);                                                        \
+		if (err__ != cudaSuccess) {                                                        \
+			::dspb200::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #expr,               \
+			                     cudaGetErrorString(err__));                               \
+			fail_action;                                                                   \
+		}                                                                                  \
+	} while (0)
+
+// ---- launch accounting (dspb200_kernel_launches()) ----------------------------------------
+extern std::atomic<long long> g_kernel_launches;
+#define LAUNCH(kernel, grid, block, smem, stream, ...)                                     \
+	do {                                                                                   \
+		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                        \
+		::dspb200::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);              \
+	} while (0)
+
+// ---- per-kernel device timing (dspb200_profile_*): CUDA events on the launching stream ------
+extern std::atomic<int> g_profile_on;
+void prof_mark(const char *name, cudaStream_t st, bool begin);
+struct ProfScope {
+	const char *name;
+	cudaStream_t st;
+	bool on;
+	ProfScope(const char *n, cudaStream_t s) : name(n), st(s), on(g_profile_on.load(std::memory_order_relaxed) != 0)
+	{
+		if (on) prof_mark(name, st, true);
+	}
+	~ProfScope()
+	{
+		if (on) prof_mark(name, st, false);
+	}
+};
+
+// ---- device memory helpers ------------------------------------------------------------------
+template <typename T>
+static inline T *dev_alloc(size_t n, bool zero = true)
+{
+	T *p = nullptr;
+	if (n == 0) n = 1;
+	cudaError_t err = cudaMalloc((void **) &p, n * sizeof(T));
+	if (err != cudaSuccess) {
+		set_error("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(err));
+		return nullptr;
+	}
+	if (zero) {
+		// allocation is rare; make the clear visible to every (non-blocking) stream
+		cudaMemset(p, 0, n * sizeof(T));
+		cudaDeviceSynchronize();
+	}
+	return p;
+}
+
+static inline void dev_free(void *p)
+{
+	if (p) cudaFree(p);
+}
+
+static inline int ceil_div(long a, long b) { return (int) ((a + b - 1) / b); }
+
+// ---- one operator instance on one shard (one GPU, one contiguous channel slab) -------------
+struct Op {
+	int channels = 0;      // channels of this shard's slab
+	int fs_in = 0, fs_out = 0;
+	bool inplace_ok = true;   // run() accepts in == out
+	virtual ~Op() {}
+	virtual const char *name() const = 0;
+	// frames in -> frames out; in/out are device pointers to interleaved [frames][channels]
+	virtual long run(long frames, const double *in, double *out, cudaStream_t st) = 0;
+	virtual long max_out_frames(long in_frames) const { return in_frames; }
+	virtual void reset(cudaStream_t st) = 0;
+	// resample.c:163-188: flush what the operator still holds.  `zeros` is scratch for `frames`
+	// frames of silence.  Returns frames written to `out`, -1 when dry, -2 on error.
+	virtual long drain2(long frames, double *zeros, double *out, cudaStream_t st)
+	{
+		(void) frames; (void) zeros; (void) out; (void) st;
+		return -1;
+	}
+};
+
+// twiddle table exp(-2 pi i t / (2N)), t in [0, 2N), resident on the current device
+const double2 *twiddles_2n(int N);
+
+}  // namespace dspb200

@@ -1,0 +1,190 @@
+"""GPU tier: seeded inputs at sizes beyond the golden fixtures against the oracle (the compiled
+reference when it travelled, else the numpy restatement), plus size-independent properties at
+BASELINE.json's full sizes (impulse -> IR, linearity)."""
+import numpy as np
+import pytest
+
+from conftest import rms
+
+pytestmark = pytest.mark.gpu
+RMS_TOL = 1e-10
+
+
+def eq_coefs(gpu_lib, fs, n_stages):
+    f = [31.25, 62.5, 125, 250, 500, 1000, 2000, 4000, 8000, 16000]
+    g = [-2, 1.5, -1, 2, -1.5, 1, -2, 1.5, -1, 2]
+    return np.array([gpu_lib.biquad_design(13, fs, f[i], 1.4, g[i]) for i in range(n_stages)])
+
+
+def test_biquad_c2_cascade(gpu_lib):
+    """Config 2 in miniature: 10-stage eq cascade, 64 ch, 4096-frame blocks, sweep + per-channel tones."""
+    from oracle import restate
+    fs, C, F = 48000, 64, 4096
+    coefs = eq_coefs(gpu_lib, fs, 10)
+    x = restate.sgen_sine(fs, C, 3 * F, 20.0, 20000.0) * 0.25
+    t = np.arange(3 * F)[:, None] / fs
+    x += 0.25 * np.sin(2 * np.pi * (100.0 + np.arange(C)[None, :]) * t)
+    want = restate.biquad_cascade(x, coefs)
+    ch = gpu_lib.Chain(fs, C).add_biquad(coefs)
+    got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, 3 * F, F)])
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+    # ragged calls, same stream
+    ch.reset()
+    cuts = [0, 1, 33, 100, 4196, 4197, 9000, 3 * F]
+    got2 = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
+    assert rms(got2 - want) <= RMS_TOL
+    ch.close()
+
+
+def test_biquad_per_channel_coefficients_and_long_cascade(gpu_lib):
+    from oracle import restate
+    fs, C, S = 44100, 7, 20      # 20 stages -> two fused operators of <= 16
+    rng = np.random.default_rng(3)
+    coefs = np.zeros((S, C, 5))
+    for s in range(S):
+        for c in range(C):
+            coefs[s, c] = gpu_lib.biquad_design(13, fs, 40.0 * (1.5 ** s) + 3 * c, 0.7 + 0.1 * c, rng.uniform(-6, 6))
+    coefs[3, 2] = [1, 0, 0, 0, 0]
+    x = rng.standard_normal((5000, C)) * 0.1
+    want = restate.biquad_cascade(x, coefs)
+    ch = gpu_lib.Chain(fs, C).add_biquad(coefs)
+    assert ch.n_ops == 2
+    got = np.concatenate([ch.run(x[i:i + 999]).copy() for i in range(0, 5000, 999)])
+    assert rms(got - want) <= RMS_TOL
+    ch.close()
+
+
+@pytest.mark.parametrize("block", [64, 1000, 1024, 2048, 4096])
+def test_fir_p_block_sizes(gpu_lib, block):
+    from oracle import restate
+    fs, C, taps = 48000, 6, 5000
+    rng = np.random.default_rng(block)
+    h = np.stack([restate.bench_ir(taps, c) for c in range(4)], axis=1)
+    sel = [1, 1, 0, 1, 0, 1]
+    N = 6 * 4096 + 123
+    x = rng.standard_normal((N, C)) * 0.2
+    want = restate.fir_stream(x, h, selector=sel)
+    ch = gpu_lib.Chain(fs, C).add_fir(h, selector=sel)
+    got = np.concatenate([ch.run(x[i:i + block]).copy() for i in range(0, N, block)])
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+    assert np.array_equal(got[:, 2], x[:, 2]) and np.array_equal(got[:, 4], x[:, 4])
+    ch.close()
+
+
+def test_fir_p_ragged_calls_and_partition_hint(gpu_lib):
+    from oracle import restate
+    fs, C, taps = 48000, 3, 3000
+    rng = np.random.default_rng(11)
+    h = restate.bench_ir(taps)
+    N = 20000
+    x = rng.standard_normal((N, C)) * 0.2
+    want = restate.fir_stream(x, h)
+    for hint in (256, 1024):
+        ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=hint)
+        cuts = sorted(set([0, N] + list(rng.integers(1, N, 25))))
+        got = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
+        assert rms(got - want) <= RMS_TOL, (hint, rms(got - want))
+        ch.close()
+
+
+def test_fir_latency_ring(gpu_lib):
+    """fir.c's FFT path: same convolution, delayed by len = next_fast_fftw_len(taps)."""
+    from oracle import restate
+    fs, C, taps = 48000, 2, 700
+    rng = np.random.default_rng(5)
+    h = restate.bench_ir(taps)
+    L = restate.next_fast_fftw_len(taps)
+    x = rng.standard_normal((9000, C)) * 0.2
+    want = restate.fir_stream(x, h, latency=L)
+    for block in (100, 512, 3000):
+        ch = gpu_lib.Chain(fs, C).add_fir(h, latency=L)
+        got = np.concatenate([ch.run(x[i:i + block]).copy() for i in range(0, 9000, block)])
+        assert rms(got - want) <= RMS_TOL, block
+        ch.close()
+
+
+@pytest.mark.parametrize("rates", [(44100, 48000), (48000, 44100), (48000, 96000), (96000, 48000), (44100, 32000)])
+def test_resample_ratios(gpu_lib, have_ref, rates):
+    from oracle import restate
+    fi, fo = rates
+    C = 5
+    rng = np.random.default_rng(fi + fo)
+    x = rng.standard_normal((9000, C)) * 0.3
+    x[:, 0] = np.sin(2 * np.pi * 1000.0 * np.arange(9000) / fi)
+    if have_ref:
+        from oracle import ref
+        want, wcounts = ref.RefChain("resample %d" % fo, fi, C).process(x, 1024)
+    else:
+        want, wcounts = restate.Resampler(fi, fo, C).process(x, 1024)
+    ch = gpu_lib.Chain(fi, C).add_resample(fo)
+    got, counts = ch.process(x, 1024)
+    assert counts == list(wcounts)
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+    ch.close()
+
+
+def test_full_size_impulse_response_property(gpu_lib):
+    """Headline shape (256 ch x 131072 taps, per-channel IR, 4096-frame blocks): a delta in gives the
+    IR back -- a size-independent known answer."""
+    from oracle import restate
+    fs, C, taps, F = 48000, 256, 131072, 4096
+    h = np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
+    ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
+    x = np.zeros((F, C))
+    x[5, :] = 1.0
+    x[7, 3] = -0.5
+    outs = [ch.run(x).copy()]
+    z = np.zeros((F, C))
+    for _ in range(taps // F):
+        outs.append(ch.run(z).copy())
+    y = np.concatenate(outs)
+    want = np.zeros_like(y)
+    want[5:5 + taps] = h
+    want[7:7 + taps, 3] += -0.5 * h[:, 3]
+    assert np.max(np.abs(y - want)) <= 1e-13
+    ch.close()
+
+
+def test_full_size_linearity_property(gpu_lib):
+    """conv(a x1 + b x2) == a conv(x1) + b conv(x2) on the headline shape with a shared IR."""
+    from oracle import restate
+    fs, C, taps, F = 48000, 256, 131072, 4096
+    h = restate.bench_ir(taps)
+    rng = np.random.default_rng(9)
+    x1 = rng.standard_normal((3 * F, C)) * 0.2
+    x2 = rng.standard_normal((3 * F, C)) * 0.2
+
+    def conv(x):
+        ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
+        y = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, 3 * F, F)])
+        ch.close()
+        return y
+    y1, y2, y12 = conv(x1), conv(x2), conv(0.5 * x1 - 2.0 * x2)
+    assert rms(y12 - (0.5 * y1 - 2.0 * y2)) <= 1e-13
+    # and one channel against the oracle's plain convolution
+    want = restate.fir_stream(x1[:, 17:18], h)
+    assert rms(y1[:, 17:18] - want) <= RMS_TOL
+
+
+def test_device_resident_mode(gpu_lib):
+    """Mode D (run_device on torch-owned buffers and stream) equals mode A."""
+    import torch
+    from oracle import restate
+    fs, C, F = 48000, 16, 1024
+    h = restate.bench_ir(3000)
+    coefs = eq_coefs(gpu_lib, fs, 4)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((4 * F, C)) * 0.2
+    a = gpu_lib.Chain(fs, C).add_biquad(coefs).add_fir(h, block_hint=F)
+    b = gpu_lib.Chain(fs, C).add_biquad(coefs).add_fir(h, block_hint=F)
+    ya = np.concatenate([a.run(x[i:i + F]).copy() for i in range(0, 4 * F, F)])
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for i in range(0, 4 * F, F):
+        d = torch.from_numpy(x[i:i + F].copy()).cuda()
+        n = b.run_device(0, F, d.data_ptr(), d.data_ptr(), st)
+        assert n == F
+        outs.append(d.cpu().numpy())
+    assert np.array_equal(ya, np.concatenate(outs))
+    a.close()
+    b.close()
