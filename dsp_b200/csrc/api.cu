@@ -218,7 +218,7 @@ struct dspb200_chain {
 	int n_ops = 0;
 	std::vector<std::unique_ptr<Shard>> shards;
 	std::vector<std::pair<void *, size_t>> registered;    // host ranges pinned by us
-	bool pin_host = true;
+	bool pin_host = false;
 
 	~dspb200_chain()
 	{
@@ -305,8 +305,11 @@ dspb200_chain *dspb200_chain_create(int fs, int channels, const int *devices, in
 	std::unique_ptr<dspb200_chain> c(new dspb200_chain());
 	c->fs = c->out_fs = fs;
 	c->channels = channels;
+	// Page-locking the CALLER's buffers is opt-in (DSP_B200_PIN=1; the C shim turns it on for the
+	// frontends' long-lived block buffers): a stale registration over recycled heap memory makes
+	// later copies fail, so arbitrary callers get plain pageable copies.
 	const char *pin = getenv("DSP_B200_PIN");
-	c->pin_host = !(pin && pin[0] == '0');
+	c->pin_host = (pin && pin[0] == '1');
 	for (int i = 0; i < n_shards; ++i) {
 		std::unique_ptr<Shard> s(new Shard());
 		s->device = devices[(long) i * n_devices / n_shards];
@@ -521,7 +524,7 @@ long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const do
 	Shard *s = c->shards[shard].get();
 	CUDA_TRY(cudaSetDevice(s->device), return -1);
 	if (s->ensure_cap(frames)) return -1;
-	cudaStream_t st = stream ? (cudaStream_t) stream : s->stream;
+	cudaStream_t st = (cudaStream_t) stream;   // NULL = the legacy default stream, as everywhere in CUDA
 	return s->run_ops(0, frames, d_in, d_out, false, st);
 }
 

@@ -12,12 +12,14 @@ artefact for the reference's own frontends is the C shim under shim/, not this f
 code that is NOT part of the accelerated path and stays the reference's C in a real deployment
 (the chain parser, `align`, drain bookkeeping) is restated here only as far as tests need it.
 """
+import importlib
 import math
 import os
 
 import numpy as np
 
-from . import lib as _lib
+# the package re-exports a FUNCTION named lib, so fetch the submodule explicitly
+_lib = importlib.import_module(".lib", __package__)
 
 BIQUAD_TYPES = {
     # name -> (type number biquad.h:30-52, positional args)

@@ -101,7 +101,7 @@ long dspb200_chain_max_out_frames(const dspb200_chain *c, long in_frames);
 long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, double *out);
 
 /* Mode D: one shard, device-resident interleaved buffers of that shard's channel count,
- * enqueued on `stream` (a cudaStream_t; NULL = the shard's own stream), asynchronous.
+ * enqueued on `stream` (a cudaStream_t; NULL = the legacy default stream), asynchronous.
  * d_in == d_out allowed only when no operator changes the frame count.  Returns output frames. */
 long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const double *d_in,
                               double *d_out, void *stream);
