@@ -342,10 +342,15 @@ int dspb200_chain_absorb(dspb200_chain *dest, dspb200_chain *src)
 		Shard &a = *dest->shards[i], &b = *src->shards[i];
 		cudaSetDevice(b.device);
 		cudaStreamSynchronize(b.stream);
-		for (auto &op : b.ops) a.ops.push_back(std::move(op));
+		for (auto &op : b.ops) {
+			// cascaded biquads collapse into one fused operator (biquad.cu); everything else queues up
+			Op *fused = a.ops.empty() ? nullptr : fuse_biquad_ops(a.ops.back().get(), op.get());
+			if (fused) a.ops.back().reset(fused);
+			else a.ops.push_back(std::move(op));
+		}
 		b.ops.clear();
 	}
-	dest->n_ops += src->n_ops;
+	dest->n_ops = (int) dest->shards[0]->ops.size();
 	dest->out_fs = src->out_fs;
 	src->n_ops = 0;
 	src->out_fs = src->fs;

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(128) k_bq_scan(const double *__restrict__ M, c
 
 struct BiquadOp : Op {
 	int S = 0, D = 0;
+	std::vector<double> h_coefs;   // [S][C][5] as handed in (kept so neighbouring cascades can be fused)
 	double *d_coef = nullptr, *d_M = nullptr, *d_zstate = nullptr, *d_b = nullptr, *d_zin = nullptr;
 	long chunk_cap = 0;
 
@@ -161,6 +162,7 @@ Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 	std::unique_ptr<BiquadOp> op(new BiquadOp());
 	const int C = slab_channels, S = n_stages, D = 2 * n_stages;
 	op->channels = C; op->fs_in = op->fs_out = fs; op->S = S; op->D = D;
+	op->h_coefs.assign(coefs, coefs + (size_t) S * C * 5);
 
 	// coefs arrive as [stage][channel][5]; device wants [stage][5][channel]
 	std::vector<double> dev_coef((size_t) S * 5 * C), M((size_t) C * D * D);
@@ -187,6 +189,17 @@ Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 	CUDA_TRY(cudaMemcpy(op->d_coef, dev_coef.data(), dev_coef.size() * sizeof(double), cudaMemcpyHostToDevice), return nullptr);
 	CUDA_TRY(cudaMemcpy(op->d_M, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice), return nullptr);
 	return op.release();
+}
+
+// Two adjacent cascades over the same slab become one operator (one pass over the block) when
+// the state still fits one lane per component.  Only legal before the first run()/after reset.
+Op *fuse_biquad_ops(Op *a, Op *b)
+{
+	BiquadOp *x = dynamic_cast<BiquadOp *>(a), *y = dynamic_cast<BiquadOp *>(b);
+	if (!x || !y || x->channels != y->channels || x->fs_in != y->fs_in || x->S + y->S > BQ_MAX_STAGES) return nullptr;
+	std::vector<double> all(x->h_coefs);
+	all.insert(all.end(), y->h_coefs.begin(), y->h_coefs.end());
+	return make_biquad_op(x->channels, x->fs_in, x->S + y->S, all.data());
 }
 
 }  // namespace dspb200

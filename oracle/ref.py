@@ -13,19 +13,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libdspref.so")
 CLI_PATH = os.path.join(_HERE, "_ref", "dsp_ref")
 
-_lib = None
+_libs = {}
 
 
 def available():
     return os.path.exists(LIB_PATH)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not available():
-            raise RuntimeError("oracle/_ref/libdspref.so missing: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(LIB_PATH)
+def lib(path=None):
+    """The reference driver library.  `path` selects another build with the same driver API
+    (tests/dropin builds the reference chain runtime around the GPU effects)."""
+    path = path or LIB_PATH
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise RuntimeError("%s missing: run `make -C oracle ref` where /root/reference exists" % path)
+        L = C.CDLL(path)
         dp = C.POINTER(C.c_double)
         L.dspref_set_loglevel.argtypes = [C.c_int]
         L.dspref_chain_new.restype = C.c_void_p
@@ -56,8 +58,8 @@ def lib():
         L.dspref_biquad_design.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, dp]
         L.dspref_next_fast_fftw_len.restype = C.c_long
         L.dspref_next_fast_fftw_len.argtypes = [C.c_long]
-        _lib = L
-    return _lib
+        _libs[path] = L
+    return _libs[path]
 
 
 def _dp(a):
@@ -67,8 +69,8 @@ def _dp(a):
 class RefChain:
     """A reference effects chain built from a chain string, e.g. "gain -6 eq 1k 1.0 3"."""
 
-    def __init__(self, chain_str, fs, channels, dir=None):
-        self.L = lib()
+    def __init__(self, chain_str, fs, channels, dir=None, lib_path=None):
+        self.L = lib(lib_path)
         self.h = self.L.dspref_chain_new(chain_str.encode(), fs, channels, dir.encode() if dir else None)
         if not self.h:
             raise ValueError("reference failed to build chain: %r" % chain_str)
