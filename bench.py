@@ -285,26 +285,40 @@ def main():
     value = total_samples / (ms * 1e-3) / 1e6
     checksum = float(d_out.abs().sum().item())
 
-    # roofline of the dominant kernel: algorithmic bytes of one k_fir_mac launch:
-    #   per selected channel and bin: P FDL rows + (per-channel IR) P filter rows read, 1 row written, 16 B each
-    P = (a.taps + F - 1) // F
+    # roofline of the dominant kernel = the MAC of the LAST partition level (it carries almost all taps).
+    # Algorithmic bytes of one launch: per selected channel and bin, P FDL rows + (per-channel IR)
+    # P filter rows read and 1 row written, 16 B each.
+    plan = [op for op in chain.describe() if op.get("op") == "fir"][0]
+    lvl = plan["levels"][-1]
     h = 0 if a.shared_ir else 1
-    mac_bytes = C * F * 16.0 * (P * (1 + h) + 1)
+    mac_bytes = C * lvl["B"] * 16.0 * (lvl["P"] * (1 + h) + 1)
+    step_bytes = sum(C * L["B"] * 16.0 * (L["P"] * (1 + h) + 1) * (F / L["B"]) for L in plan["levels"])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "fir_mac:C%d:B%d:P%d:h%d" % (C, lvl["B"], lvl["P"], h)
+        traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = None
+    head_ms, head_n = dsp_b200.profile_read("fir_mac_head")
     if mac_n > 0:
         mac_avg_s = mac_ms / mac_n * 1e-3
         ach = mac_bytes / mac_avg_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_fir_mac", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        roofline = {"bound": "hbm", "kernel": "k_fir_mac (level B=%d, P=%d)" % (lvl["B"], lvl["P"]), "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": mac_bytes, "avg_launch_us": mac_avg_s * 1e6, "launches": mac_n,
                     "share_of_step": mac_ms / ms if ms > 0 else None,
-                    "other_kernels_us": {"k_fir_fwd": fwd_ms / max(fwd_n, 1) * 1e3, "k_fir_inv": inv_ms / max(inv_n, 1) * 1e3}}
+                    "partition_levels": plan["levels"], "mac_bytes_per_step_all_levels": step_bytes,
+                    "other_kernels_us_per_step": {"k_fir_fwd": fwd_ms / steps * 1e3, "k_fir_inv": inv_ms / steps * 1e3,
+                                                  "k_fir_mac_head": head_ms / steps * 1e3, "k_fir_level0": dsp_b200.profile_read("fir_level0")[0] / steps * 1e3, "k_fir_mac": mac_ms / steps * 1e3}}
     chain.close()
     del chain
 
@@ -340,7 +354,7 @@ def main():
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        config["l2"] = "per-step working set %.2f GB of FDL+filter spectra streamed from HBM (> 126 MB L2); %d rotating input blocks" % (mac_bytes / 1e9, n_pool)
+        config["l2"] = "per-step working set %.2f GB of FDL+filter spectra streamed from HBM (> 126 MB L2); %d rotating input blocks" % (step_bytes / 1e9, n_pool)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,

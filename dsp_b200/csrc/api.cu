@@ -9,6 +9,7 @@
 // concurrently.  There is no cross-shard data dependency, hence no collective.
 #include "common.cuh"
 #include "ops.h"
+#include "fft.cuh"
 #include "../../include/dsp_b200.h"
 #include <cmath>
 #include <map>
@@ -84,6 +85,40 @@ const double2 *twiddles_2n(int N)
 	if (!d) return nullptr;
 	CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice), return nullptr);
 	g_tw[{ dev, N }] = d;
+	return d;
+}
+
+static std::map<std::pair<int, int>, double2 *> g_ptw;   // (device, N) -> per-pass tables
+
+const double2 *twiddles_pass(int N)
+{
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return nullptr; }
+	std::lock_guard<std::mutex> lk(g_tw_lock);
+	auto it = g_ptw.find({ dev, N });
+	if (it != g_ptw.end()) return it->second;
+	std::vector<double2> h((size_t) fft_pass_table_size(N) + 1);
+	const long double pi = 3.14159265358979323846264338327950288L;
+	size_t off = 0;
+	long ns = 1;
+	for (int p = 0; p < 4 && fft_radix(N, p) != 0; ++p) {
+		const int R = fft_radix(N, p);
+		if (ns > 1) {
+			for (int mi = 0; mi < 4; ++mi)
+				for (long k = 0; k < ns; ++k) {
+					// exp(-2 pi i k 2^mi / (ns R)), argument reduced modulo one turn first
+					const long num = (k << mi) % (ns * R);
+					const long double ang = 2.0L * pi * (long double) num / (long double) (ns * R);
+					h[off + (size_t) mi * ns + k] = make_double2((double) cosl(ang), (double) -sinl(ang));
+				}
+			off += 4 * ns;
+		}
+		ns *= R;
+	}
+	double2 *d = dev_alloc<double2>(h.size(), false);
+	if (!d) return nullptr;
+	CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice), return nullptr);
+	g_ptw[{ dev, N }] = d;
 	return d;
 }
 
@@ -355,6 +390,23 @@ int dspb200_chain_absorb(dspb200_chain *dest, dspb200_chain *src)
 	src->n_ops = 0;
 	src->out_fs = src->fs;
 	return 0;
+}
+
+int dspb200_chain_describe(const dspb200_chain *c, char *buf, size_t len)
+{
+	if (!c || !buf || len == 0) return -1;
+	std::string s = "[";
+	if (!c->shards.empty()) {
+		bool first = true;
+		for (const auto &op : c->shards[0]->ops) {
+			if (!first) s += ",";
+			s += op->describe();
+			first = false;
+		}
+	}
+	s += "]";
+	snprintf(buf, len, "%s", s.c_str());
+	return (int) s.size();
 }
 
 int dspb200_chain_n_ops(const dspb200_chain *c) { return c ? c->n_ops : 0; }

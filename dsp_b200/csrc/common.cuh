@@ -86,6 +86,7 @@ struct Op {
 	bool inplace_ok = true;   // run() accepts in == out
 	virtual ~Op() {}
 	virtual const char *name() const = 0;
+	virtual std::string describe() const { return std::string("{\"op\":\"") + name() + "\"}"; }
 	// frames in -> frames out; in/out are device pointers to interleaved [frames][channels]
 	virtual long run(long frames, const double *in, double *out, cudaStream_t st) = 0;
 	virtual long max_out_frames(long in_frames) const { return in_frames; }
@@ -101,5 +102,7 @@ struct Op {
 
 // twiddle table exp(-2 pi i t / (2N)), t in [0, 2N), resident on the current device
 const double2 *twiddles_2n(int N);
+// per-pass butterfly twiddles of the N-point transform (layout: fft.cuh, fft_pass_table_size())
+const double2 *twiddles_pass(int N);
 
 }  // namespace dspb200

@@ -4,43 +4,106 @@
 //   fir_p_effect_run  fir_p.c:127-181   out = in * h, zero latency, any frames per call
 //   fir_effect_run    fir.c:109-149     out = (in * h) delayed by len frames
 //   fir_direct_effect_run fir.c:43-62   out = in * h, zero latency (short filters)
-// The reference's partition plan (32-tap direct head + <=4 FFT groups, fir_p.c:290-335) is a
-// CPU latency device; its output is exactly the linear convolution, which is what is kept.
+// The reference's partition plan (32-tap direct head + <=4 FFT groups on worker threads,
+// fir_p.c:290-335) is a CPU latency device; its output is exactly the linear convolution, which is
+// what is kept.
 //
-// B200 formulation: uniform partitions of B frames (B = power of two, 64..8192), overlap-add
-// framing, frequency-domain delay line (FDL) per selected channel:
-//   block j complete:  X_j = RFFT_2B([x_j | 0])                      -> FDL slot j mod P   (k_fir_fwd)
-//                      S_j = sum_{p<P} X_{j-p} . H_p                 streams FDL + H      (k_fir_mac)
-//                      s_j = IRFFT_2B(S_j); out_j = s_j[0:B) + carry; carry = s_j[B:2B)  (k_fir_inv)
-// Spectra are stored "packed": B complex per row, bin 0 = (DC.re, Nyquist.re); rows are
-// 16*B bytes, so every row is 128-byte aligned and a warp reads 512 contiguous bytes.
+// B200 formulation.  Per selected channel the stream is kept in a contiguous history ring
+// (k_fir_stash transposes each interleaved block into it).  The filter is cut into LEVELS of
+// doubling partition size, all overlap-add with a frequency-domain delay line (FDL):
+//   level 0: partition B0 = the call's block size (power of two <= 8192), taps [0, 2 B0)  (all taps if
+//            the filter is short), advanced on every block of B0 frames
+//   level l: partition B_l = 2^l B0 <= 8192, taps [B_l, 2 B_l) -- the last level takes all remaining
+//            taps in P_l partitions -- advanced whenever B_l frames have accumulated; a level's result
+//            for its block J is due one block period later (its taps start at B_l), so it is simply
+//            computed when block J completes and added during block J+1 ("pend" buffer)
+// For one level with partition B:  X_j = RFFT_2B([x_j | 0]) -> FDL slot j mod P           (k_fir_fwd)
+//                                  S_j = sum_{p<P} X_{j-p} . H_p   streams FDL + H          (k_fir_mac)
+//                                  s_j = IRFFT_2B(S_j); y_j = s_j[0:B) + carry; carry = s_j[B:2B)  (k_fir_inv)
+// Spectra are stored "packed": B complex per row, bin 0 = (DC.re, Nyquist.re); rows are 16 B bytes
+// long, 128-byte aligned.  The MAC is the HBM-bound kernel; larger partitions for the late taps cut
+// its bytes per sample (131072 taps, 4096-frame blocks: 1040 B/sample uniform -> 576 B/sample).
 //
-// Calls that are not whole aligned blocks take the general path, which is exact for ANY
-// frames-per-call pattern: with R_j = sum_{1<=p<P} X_{j-p} . H_p (past blocks only)
-//   out_j[m] = pre_j[m] + sum_{r<=m} x_j[r] h[m-r],   pre_j = IRFFT(R_j)[0:B) + carry_{j-1}
-// i.e. a time-domain head over the samples of the still-incomplete block (k_fir_head) on top
-// of a precomputed contribution of all completed blocks; when the block completes, X_j enters
-// the FDL and carry_j is refreshed.  Both paths share {FDL, carry, block counter}.
+// Calls that are not whole aligned blocks take the general path, exact for ANY frames-per-call
+// pattern: with R_j = sum_{1<=p<P0} X_{j-p} . H_p (completed level-0 blocks only)
+//   out_j[m] = IRFFT(R_j)[m] + carry_{j-1}[m] + pend(m) + sum_{r<=m} x_j[r] h[m-r]
+// i.e. a time-domain head over the samples of the still-incomplete block (k_fir_head) on top of the
+// precomputed contribution of everything that is complete.  Levels >= 1 never need a head: they only
+// ever look at completed blocks.  All paths share {history, FDLs, carries, block counters}.
 #include "common.cuh"
 #include "fft.cuh"
 #include "ops.h"
 
 namespace dspb200 {
 
+constexpr int FIR_MAX_LEVELS = 8;
+constexpr int FIR_MAX_B = 8192;
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
+
+// interleaved block -> per-channel contiguous history ring; tile transpose through shared memory
+__global__ void __launch_bounds__(256) k_fir_stash(const double *__restrict__ in, long stride, const int *__restrict__ ch_map,
+                                                   double *__restrict__ hist, long hist_len, long pos, int frames, int n_sel)
+{
+	__shared__ double tile[32][33];
+	const int f0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int f = f0 + r, s = s0 + tx;
+		tile[r][tx] = (f < frames && s < n_sel) ? in[(long) f * stride + ch_map[s]] : 0.0;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int s = s0 + r, f = f0 + tx;
+		if (s < n_sel && f < frames) hist[(long) s * hist_len + pos + f] = tile[tx][r];
+	}
+}
+
+struct PendArgs {
+	int n;
+	const double *buf[FIR_MAX_LEVELS];   // [s][len]
+	int len[FIR_MAX_LEVELS];
+	int off[FIR_MAX_LEVELS];             // offset of this call's first frame inside the level's period
+};
+
+// per-channel contiguous result (+ pending contributions of the larger levels) -> interleaved block
+__global__ void __launch_bounds__(256) k_fir_unstash(const double *__restrict__ y, long y_len, PendArgs pend, double *__restrict__ out,
+                                                     long stride, const int *__restrict__ ch_map, int frames, int n_sel)
+{
+	__shared__ double tile[32][33];
+	const int f0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int s = s0 + r, f = f0 + tx;
+		double v = 0.0;
+		if (s < n_sel && f < frames) {
+			v = y[(long) s * y_len + f];
+			for (int l = 0; l < pend.n; ++l) v += pend.buf[l][(long) s * pend.len[l] + pend.off[l] + f];
+		}
+		tile[r][tx] = v;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int f = f0 + r, s = s0 + tx;
+		if (f < frames && s < n_sel) out[(long) f * stride + (ch_map ? ch_map[s] : s)] = tile[tx][r];
+	}
+}
+
 struct FwdArgs {
-	const double *in;       // time-domain source
-	long stride;            // elements between consecutive frames
-	const int *ch_map;      // selected-channel index -> element offset multiplier (NULL: s)
-	long ch_mul;
+	const double *in;       // per-channel contiguous source
+	long ch_stride;         // elements between channels (0: one shared channel)
 	long valid;             // frames available (<= B); the rest is zero
 	double2 *spec;          // destination rows
 	long spec_ch_stride;    // double2 elements between channels
 	int slot;               // row within the channel
-	const double2 *tw;
-	int s0, s1;             // selected-channel range handled by this launch
+	const double2 *tw, *ptw;   // split twiddles W_2N^k, per-pass butterfly twiddles
+	int n_ch;
 };
 
 template <int N>
@@ -49,23 +112,24 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_fwd(FwdArgs a)
 	extern __shared__ double2 smem[];
 	constexpr int T = FftCfg<N>::T, CPB = FftCfg<N>::CPB;
 	const int g = threadIdx.x / T, t = threadIdx.x % T;
-	const int s = a.s0 + blockIdx.x * CPB + g;
-	const bool active = s < a.s1;
-	double2 *buf = smem + (size_t) g * N;
+	const int s = blockIdx.x * CPB + g;
+	const bool active = s < a.n_ch;
+	double2 *buf = smem + (size_t) g * FftCfg<N>::STRIDE;
 
 	if (active) {
-		const long off = (long) (a.ch_map ? a.ch_map[s] : s) * a.ch_mul;
-		const double *x = a.in + off;
+		const double *xs = a.in + (long) s * a.ch_stride;
+		const bool aligned = ((reinterpret_cast<size_t>(xs) & 15) == 0);
+		const double2 *x = reinterpret_cast<const double2 *>(xs);
 		for (int n = t; n < N / 2; n += T) {
-			const long f0 = 2L * n;
-			const double x0 = (f0 < a.valid) ? x[f0 * a.stride] : 0.0;
-			const double x1 = (f0 + 1 < a.valid) ? x[(f0 + 1) * a.stride] : 0.0;
-			buf[n] = make_double2(x0, x1);
-			buf[n + N / 2] = make_double2(0.0, 0.0);
+			double2 v;
+			if (aligned && 2L * n + 1 < a.valid) v = x[n];
+			else v = make_double2((2L * n < a.valid) ? xs[2 * n] : 0.0, (2L * n + 1 < a.valid) ? xs[2 * n + 1] : 0.0);
+			buf[spad(n)] = v;
+			buf[spad(n + N / 2)] = make_double2(0.0, 0.0);
 		}
 	}
 	__syncthreads();
-	fft_forward_smem<N>(buf, a.tw, t);
+	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
 		double2 *X = a.spec + (long) s * a.spec_ch_stride + (long) a.slot * N;
 		for (int k = t; k <= N / 2; k += T) {
@@ -74,7 +138,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_fwd(FwdArgs a)
 				X[0] = make_double2(z0.x + z0.y, z0.x - z0.y);
 			}
 			else {
-				const double2 zk = buf[k], zn = buf[N - k];
+				const double2 zk = buf[spad(k)], zn = buf[spad(N - k)];
 				const double2 e = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
 				const double2 o = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
 				const double2 wo = cmul(__ldg(&a.tw[k]), o);
@@ -89,14 +153,12 @@ enum { INV_OUT = 1, INV_UPDATE_CARRY = 2 };
 
 struct InvArgs {
 	const double2 *Y;       // [s][N] packed spectra
-	double *out;            // destination of first half + carry (INV_OUT)
-	long stride;
-	const int *ch_map;
-	long ch_mul;
+	double *out;            // INV_OUT: out[s * out_ch_stride + i] = first half + carry, i < B
+	long out_ch_stride;     // even
 	double *carry;          // [s][B]
 	int flags;
-	const double2 *tw;
-	int s0, s1;
+	const double2 *tw, *ptw;
+	int n_ch;
 };
 
 template <int N>
@@ -105,9 +167,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 	extern __shared__ double2 smem[];
 	constexpr int T = FftCfg<N>::T, CPB = FftCfg<N>::CPB;
 	const int g = threadIdx.x / T, t = threadIdx.x % T;
-	const int s = a.s0 + blockIdx.x * CPB + g;
-	const bool active = s < a.s1;
-	double2 *buf = smem + (size_t) g * N;
+	const int s = blockIdx.x * CPB + g;
+	const bool active = s < a.n_ch;
+	double2 *buf = smem + (size_t) g * FftCfg<N>::STRIDE;
 
 	if (active) {
 		const double2 *Y = a.Y + (long) s * N;
@@ -123,33 +185,133 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 				const double2 d = make_double2(0.5 * (xk.x - xn.x), 0.5 * (xk.y + xn.y));
 				const double2 o = cmul(cconj(__ldg(&a.tw[k])), d);
 				// Z[k] = E + iO, Z[N-k] = conj(E) + i conj(O); store conj(Z)
-				buf[k] = make_double2(e.x - o.y, -(e.y + o.x));
-				buf[N - k] = make_double2(e.x + o.y, -(o.x - e.y));
+				buf[spad(k)] = make_double2(e.x - o.y, -(e.y + o.x));
+				buf[spad(N - k)] = make_double2(e.x + o.y, -(o.x - e.y));
 			}
 		}
 	}
 	__syncthreads();
-	fft_forward_smem<N>(buf, a.tw, t);
+	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
 		const double scale = 1.0 / N;
-		const long off = (long) (a.ch_map ? a.ch_map[s] : s) * a.ch_mul;
-		double *carry = a.carry + (long) s * N;
+		double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
+		double2 *out = reinterpret_cast<double2 *>(a.out + (long) s * a.out_ch_stride);
 		for (int n = t; n < N / 2; n += T) {
-			const double2 lo = buf[n], hi = buf[n + N / 2];
+			const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
 			if (a.flags & INV_OUT) {
-				const double2 c = *reinterpret_cast<const double2 *>(carry + 2 * n);
-				a.out[(2L * n) * a.stride + off] = fma(lo.x, scale, c.x);
-				a.out[(2L * n + 1) * a.stride + off] = fma(-lo.y, scale, c.y);
+				const double2 c = carry[n];
+				out[n] = make_double2(fma(lo.x, scale, c.x), fma(-lo.y, scale, c.y));
 			}
-			if (a.flags & INV_UPDATE_CARRY)
-				*reinterpret_cast<double2 *>(carry + 2 * n) = make_double2(hi.x * scale, -hi.y * scale);
+			if (a.flags & INV_UPDATE_CARRY) carry[n] = make_double2(hi.x * scale, -hi.y * scale);
+		}
+	}
+}
+
+// Level 0 in one kernel when it has few partitions (P <= 4; P = 2 whenever larger levels exist):
+// forward transform of the new block, its spectrum into the FDL, S = X_j H_0 + sum_{p>=1} X_{j-p} H_p
+// formed by the thread that owns the bin pair (k, N-k) straight from registers, inverse transform in
+// the same shared-memory buffer, overlap-add epilogue.  One launch instead of three and no spectrum
+// round trip through HBM.
+struct L0Args {
+	const double *in;        // per-channel contiguous block (history ring)
+	long in_ch_stride;
+	double2 *fdl;            // [s][P][N]
+	const double2 *H;        // [s or 0][P][N]
+	long h_ch_stride;
+	int P, slot;
+	double *out;             // [s][out_ch_stride]: first half + carry
+	long out_ch_stride;
+	double *carry;           // [s][N]
+	const double2 *tw, *ptw;
+	int n_ch;
+};
+
+__device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 h)
+{
+	return make_double2(fma(x.x, h.x, fma(-x.y, h.y, acc.x)), fma(x.x, h.y, fma(x.y, h.x, acc.y)));
+}
+
+template <int N>
+__global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
+{
+	extern __shared__ double2 smem[];
+	constexpr int T = FftCfg<N>::T, CPB = FftCfg<N>::CPB;
+	const int g = threadIdx.x / T, t = threadIdx.x % T;
+	const int s = blockIdx.x * CPB + g;
+	const bool active = s < a.n_ch;
+	double2 *buf = smem + (size_t) g * FftCfg<N>::STRIDE;
+
+	if (active) {
+		const double2 *x = reinterpret_cast<const double2 *>(a.in + (long) s * a.in_ch_stride);
+		for (int n = t; n < N / 2; n += T) {
+			buf[spad(n)] = x[n];
+			buf[spad(n + N / 2)] = make_double2(0.0, 0.0);
+		}
+	}
+	__syncthreads();
+	fft_forward_smem<N>(buf, a.ptw, t);
+	if (active) {
+		double2 *fdl = a.fdl + (long) s * a.P * N;
+		const double2 *H = a.H + (long) s * a.h_ch_stride;
+		double2 *X = fdl + (long) a.slot * N;
+		for (int k = t; k <= N / 2; k += T) {
+			if (k == 0) {
+				const double2 z0 = buf[0];
+				const double2 x0 = make_double2(z0.x + z0.y, z0.x - z0.y);
+				X[0] = x0;
+				const double2 h0 = H[0];
+				double2 S = make_double2(x0.x * h0.x, x0.y * h0.y);   // packed: DC and Nyquist are separate real products
+				for (int p = 1; p < a.P; ++p) {
+					const int sl = (a.slot - p < 0) ? a.slot - p + a.P : a.slot - p;
+					const double2 xp = fdl[(long) sl * N], hp = H[(long) p * N];
+					S.x = fma(xp.x, hp.x, S.x);
+					S.y = fma(xp.y, hp.y, S.y);
+				}
+				buf[0] = make_double2(0.5 * (S.x + S.y), -0.5 * (S.x - S.y));
+			}
+			else {
+				const int n = N - k;
+				const double2 zk = buf[spad(k)], zn = buf[spad(n)];
+				const double2 e0 = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+				const double2 o0 = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
+				const double2 w = __ldg(&a.tw[k]);
+				const double2 wo = cmul(w, o0);
+				const double2 xk = cadd(e0, wo), xn = cconj(csub(e0, wo));
+				X[k] = xk;
+				if (k != N / 2) X[n] = xn;
+				double2 Sk = cmul(xk, H[k]), Sn = cmul(xn, H[n]);
+				for (int p = 1; p < a.P; ++p) {
+					const int sl = (a.slot - p < 0) ? a.slot - p + a.P : a.slot - p;
+					Sk = cmac(Sk, fdl[(long) sl * N + k], H[(long) p * N + k]);
+					Sn = cmac(Sn, fdl[(long) sl * N + n], H[(long) p * N + n]);
+				}
+				// inverse merge of (S[k], S[N-k]) -> conj(Z[k]), conj(Z[N-k])
+				const double2 e = make_double2(0.5 * (Sk.x + Sn.x), 0.5 * (Sk.y - Sn.y));
+				const double2 d = make_double2(0.5 * (Sk.x - Sn.x), 0.5 * (Sk.y + Sn.y));
+				const double2 o = cmul(cconj(w), d);
+				buf[spad(k)] = make_double2(e.x - o.y, -(e.y + o.x));
+				buf[spad(n)] = make_double2(e.x + o.y, -(o.x - e.y));
+			}
+		}
+	}
+	__syncthreads();
+	fft_forward_smem<N>(buf, a.ptw, t);
+	if (active) {
+		const double scale = 1.0 / N;
+		double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
+		double2 *out = reinterpret_cast<double2 *>(a.out + (long) s * a.out_ch_stride);
+		for (int n = t; n < N / 2; n += T) {
+			const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
+			const double2 c = carry[n];
+			out[n] = make_double2(fma(lo.x, scale, c.x), fma(-lo.y, scale, c.y));
+			carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 		}
 	}
 }
 
 // Y[s][k] = sum_{p in [p0,p1)} FDL[s][(slot0 - p) mod P][k] * H[s or 0][p][k]   (packed bin 0)
-// This is the HBM-streaming kernel of the engine: 32 bytes in per complex MAC (16 with a
-// shared IR, whose rows stay in L2), 4 DFMA.
+// The HBM-streaming kernel of the engine: 32 bytes in per complex MAC (16 with a shared IR, whose
+// rows stay in L2), 4 DFMA.
 struct MacArgs {
 	const double2 *fdl;   // [s][P][N]
 	const double2 *H;     // [s][P][N] or [P][N]
@@ -157,14 +319,13 @@ struct MacArgs {
 	int N, P;
 	int slot0, p0, p1;
 	long h_ch_stride;     // P*N or 0 (shared IR)
-	int s0;
 };
 
 template <bool SHARED_H>
 __global__ void __launch_bounds__(256) k_fir_mac(MacArgs a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	const int s = a.s0 + blockIdx.y;
+	const int s = blockIdx.y;
 	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
 	double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
@@ -211,32 +372,25 @@ __global__ void __launch_bounds__(256) k_fir_mac(MacArgs a)
 	a.Y[(long) s * a.N + k] = make_double2((acc0.x + acc1.x) + (acc2.x + acc3.x), (acc0.y + acc1.y) + (acc2.y + acc3.y));
 }
 
-// general path: stash the new frames of the incomplete block, per-channel contiguous
-__global__ void k_fir_stash(const double *in, long stride, const int *ch_map, double *xcur, int B, int pos, int seg, int s0)
+// general path: out[m] = pre[m] + pend(m) + sum_{r<=m} x[r] h0[m-r], m = pos+i; x = current level-0 block in the ring
+__global__ void k_fir_head(const double *hist, long hist_len, long blk_off, const double *pre, const double *h0, long h0_ch_stride,
+                           PendArgs pend, double *out, long stride, const int *ch_map, int B, int pos, int seg)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int s = s0 + blockIdx.y;
-	if (i < seg) xcur[(long) s * B + pos + i] = in[(long) i * stride + ch_map[s]];
-}
-
-// general path: out[m] = pre[m] + sum_{r<=m} xcur[r] h0[m-r], m = pos+i
-__global__ void k_fir_head(const double *xcur, const double *pre, const double *h0, long h0_ch_stride,
-                           double *out, long stride, const int *ch_map, int B, int pos, int seg, int s0)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int s = s0 + blockIdx.y;
+	const int s = blockIdx.y;
 	if (i >= seg) return;
 	const int m = pos + i;
-	const double *x = xcur + (long) s * B;
+	const double *x = hist + (long) s * hist_len + blk_off;
 	const double *h = h0 + (long) s * h0_ch_stride;
 	double acc0 = pre[(long) s * B + m], acc1 = 0.0;
+	for (int l = 0; l < pend.n; ++l) acc1 += pend.buf[l][(long) s * pend.len[l] + pend.off[l] + i];
 	int r = 0;
 	for (; r + 2 <= m + 1; r += 2) {
 		acc0 = fma(x[r], h[m - r], acc0);
 		acc1 = fma(x[r + 1], h[m - r - 1], acc1);
 	}
 	if (r <= m) acc0 = fma(x[r], h[m - r], acc0);
-	out[(long) i * stride + ch_map[s]] = acc0 + acc1;
+	out[(long) i * stride + (ch_map ? ch_map[s] : s)] = acc0 + acc1;
 }
 
 // fir.c latency: out[a] = y[a - L]; ring slot of absolute frame a is a % L
@@ -266,7 +420,7 @@ __global__ void k_delay_write(const double *y, long y_stride, double *ring, int 
 // launch helpers (dispatch on the FFT size)
 // ------------------------------------------------------------------------------------------
 template <int N>
-static int launch_fwd_n(const FwdArgs &a, cudaStream_t st)
+static int configure_n()
 {
 	static std::atomic<int> configured[64];
 	int dev = 0;
@@ -274,22 +428,39 @@ static int launch_fwd_n(const FwdArgs &a, cudaStream_t st)
 	if (!configured[dev & 63].load()) {
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_fwd<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_inv<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
+		CUDA_TRY(cudaFuncSetAttribute(k_fir_level0<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		configured[dev & 63].store(1);
 	}
-	const int n = a.s1 - a.s0;
-	if (n <= 0) return 0;
+	return 0;
+}
+
+template <int N>
+static int launch_fwd_n(const FwdArgs &a, cudaStream_t st)
+{
+	if (configure_n<N>()) return -1;
+	if (a.n_ch <= 0) return 0;
 	ProfScope prof("fir_fwd", st);
-	LAUNCH(k_fir_fwd<N>, ceil_div(n, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	LAUNCH(k_fir_fwd<N>, ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
 	return 0;
 }
 
 template <int N>
 static int launch_inv_n(const InvArgs &a, cudaStream_t st)
 {
-	const int n = a.s1 - a.s0;
-	if (n <= 0) return 0;
+	if (configure_n<N>()) return -1;
+	if (a.n_ch <= 0) return 0;
 	ProfScope prof("fir_inv", st);
-	LAUNCH(k_fir_inv<N>, ceil_div(n, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	LAUNCH(k_fir_inv<N>, ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	return 0;
+}
+
+template <int N>
+static int launch_level0_n(const L0Args &a, cudaStream_t st)
+{
+	if (configure_n<N>()) return -1;
+	if (a.n_ch <= 0) return 0;
+	ProfScope prof("fir_level0", st);
+	LAUNCH(k_fir_level0<N>, ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
 	return 0;
 }
 
@@ -307,20 +478,15 @@ static int launch_inv_n(const InvArgs &a, cudaStream_t st)
 	}
 
 static int launch_fwd(int N, const FwdArgs &a, cudaStream_t st) { DISPATCH_N(N, launch_fwd_n, a, st) }
-static int launch_inv(int N, const InvArgs &a, cudaStream_t st)
-{
-	// launch_fwd configures both kernels' shared-memory limits; make sure it ran for this N
-	FwdArgs none = {};
-	if (launch_fwd(N, none, st)) return -1;
-	DISPATCH_N(N, launch_inv_n, a, st)
-}
+static int launch_inv(int N, const InvArgs &a, cudaStream_t st) { DISPATCH_N(N, launch_inv_n, a, st) }
+static int launch_level0(int N, const L0Args &a, cudaStream_t st) { DISPATCH_N(N, launch_level0_n, a, st) }
 
-static void launch_mac(const MacArgs &a, int n_sel_range, bool shared_h, cudaStream_t st)
+static void launch_mac(const MacArgs &a, int n_sel, bool shared_h, const char *prof_name, cudaStream_t st)
 {
-	if (n_sel_range <= 0) return;
+	if (n_sel <= 0) return;
 	const int threads = (a.N < 256) ? a.N : 256;
-	dim3 grid(a.N / threads, n_sel_range);
-	ProfScope prof("fir_mac", st);
+	dim3 grid(a.N / threads, n_sel);
+	ProfScope prof(prof_name, st);
 	if (shared_h) LAUNCH(k_fir_mac<true>, grid, threads, 0, st, a);
 	else LAUNCH(k_fir_mac<false>, grid, threads, 0, st, a);
 }
@@ -331,11 +497,12 @@ static void launch_mac(const MacArgs &a, int n_sel_range, bool shared_h, cudaStr
 int test_rfft(int B, int n_ch, const double *d_in, double *d_spec, cudaStream_t st)
 {
 	FwdArgs a = {};
-	a.in = d_in; a.stride = 1; a.ch_map = nullptr; a.ch_mul = B; a.valid = B;
+	a.in = d_in; a.ch_stride = B; a.valid = B;
 	a.spec = reinterpret_cast<double2 *>(d_spec); a.spec_ch_stride = B; a.slot = 0;
 	a.tw = twiddles_2n(B);
-	if (!a.tw) return -1;
-	a.s0 = 0; a.s1 = n_ch;
+	a.ptw = twiddles_pass(B);
+	if (!a.tw || !a.ptw) return -1;
+	a.n_ch = n_ch;
 	return launch_fwd(B, a, st);
 }
 
@@ -346,11 +513,12 @@ int test_irfft(int B, int n_ch, const double *d_spec, double *d_out2B, cudaStrea
 	if (!carry) return -1;
 	InvArgs a = {};
 	a.Y = reinterpret_cast<const double2 *>(d_spec);
-	a.out = d_out2B; a.stride = 1; a.ch_map = nullptr; a.ch_mul = 2L * B;
+	a.out = d_out2B; a.out_ch_stride = 2L * B;
 	a.carry = carry; a.flags = INV_OUT | INV_UPDATE_CARRY;
 	a.tw = twiddles_2n(B);
-	a.s0 = 0; a.s1 = n_ch;
-	int r = (a.tw) ? launch_inv(B, a, st) : -1;
+	a.ptw = twiddles_pass(B);
+	a.n_ch = n_ch;
+	int r = (a.tw && a.ptw) ? launch_inv(B, a, st) : -1;
 	if (r == 0) {
 		for (int c = 0; c < n_ch && r == 0; ++c)
 			if (cudaMemcpyAsync(d_out2B + (size_t) c * 2 * B + B, carry + (size_t) c * B, B * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) r = -1;
@@ -363,79 +531,130 @@ int test_irfft(int B, int n_ch, const double *d_spec, double *d_out2B, cudaStrea
 // ------------------------------------------------------------------------------------------
 // operator
 // ------------------------------------------------------------------------------------------
+struct FirLevel {
+	int B = 0, P = 0;
+	long tap0 = 0, tap1 = 0;      // taps [tap0, tap1) of the filter
+	const double2 *tw = nullptr, *ptw = nullptr;
+	double2 *fdl = nullptr, *H = nullptr;
+	double *carry = nullptr, *pend = nullptr;
+	long blk = 0;                 // completed blocks of this level
+
+	void free_all() { dev_free(fdl); dev_free(H); dev_free(carry); dev_free(pend); }
+};
+
 struct FirOp : Op {
 	// description (host)
 	std::vector<int> h_ch_map;          // selected channel -> channel index in the slab
-	std::vector<double> h_taps;         // [filter_frames][fc] (kept until planned)
+	std::vector<double> h_taps;         // [fc][filter_frames] per-column contiguous (kept until planned)
 	int fc = 1;                         // filter channels: 1 (shared) or n_sel
 	long filter_frames = 0;
 	long latency = 0;
 	int n_sel = 0;
+	bool multilevel = true;
 
 	// plan
 	bool planned = false;
-	int B = 0, P = 0;
-	const double2 *tw = nullptr;
+	int B0 = 0, n_levels = 0;
+	FirLevel lv[FIR_MAX_LEVELS];
+	long hist_len = 0;
 
 	// device state
 	int *d_ch_map = nullptr;
-	double2 *d_fdl = nullptr, *d_H = nullptr, *d_Y = nullptr;
-	double *d_carry = nullptr, *d_xcur = nullptr, *d_pre = nullptr, *d_h0 = nullptr;
-	double *d_ring = nullptr, *d_ytmp = nullptr;
-	long ytmp_cap = 0;
-	long blk = 0;        // completed blocks
-	int pos = 0;         // frames of the current block already consumed
+	double *d_hist = nullptr, *d_ytmp = nullptr, *d_pre = nullptr, *d_h0 = nullptr;
+	double2 *d_Y = nullptr;              // [n_sel][max B]
+	double *d_ring = nullptr, *d_ltmp = nullptr;
+	long ltmp_cap = 0;
+	long abs_pos = 0;                    // frames consumed so far (level-0 block = abs_pos / B0, offset = abs_pos % B0)
 	bool pre_valid = false;
-	long abs_frames = 0; // total frames seen (delay ring phase)
 
 	const char *name() const override { return "fir"; }
 
+	std::string describe() const override
+	{
+		char buf[512];
+		int n = snprintf(buf, sizeof(buf), "{\"op\":\"fir\",\"taps\":%ld,\"n_sel\":%d,\"filter_channels\":%d,\"latency\":%ld,\"planned\":%d,\"levels\":[",
+		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
+		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
+			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
+		snprintf(buf + n, sizeof(buf) - n, "]}");
+		return buf;
+	}
+
 	~FirOp() override
 	{
-		dev_free(d_ch_map); dev_free(d_fdl); dev_free(d_H); dev_free(d_Y); dev_free(d_carry);
-		dev_free(d_xcur); dev_free(d_pre); dev_free(d_h0); dev_free(d_ring); dev_free(d_ytmp);
+		for (int l = 0; l < n_levels; ++l) lv[l].free_all();
+		dev_free(d_ch_map); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
+		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp);
 	}
 
 	int plan(long hint, cudaStream_t st)
 	{
 		int b = 64;
-		while (b * 2 <= hint && b < 8192) b *= 2;
-		B = b;
-		P = (int) ((filter_frames + B - 1) / B);
-		tw = twiddles_2n(B);
-		if (!tw) return -1;
-		const size_t rows = (size_t) n_sel * P;
-		d_fdl = dev_alloc<double2>(rows * B);
-		d_H = dev_alloc<double2>((size_t) ((fc == 1) ? 1 : n_sel) * P * B);
-		d_Y = dev_alloc<double2>((size_t) n_sel * B);
-		d_carry = dev_alloc<double>((size_t) n_sel * B);
-		d_xcur = dev_alloc<double>((size_t) n_sel * B);
-		d_pre = dev_alloc<double>((size_t) n_sel * B);
-		d_h0 = dev_alloc<double>((size_t) ((fc == 1) ? 1 : n_sel) * B);
-		if (latency > 0) d_ring = dev_alloc<double>((size_t) latency * n_sel);
-		if (!d_fdl || !d_H || !d_Y || !d_carry || !d_xcur || !d_pre || !d_h0 || (latency > 0 && !d_ring)) return -1;
-
-		// filter spectra: H[c][p] = RFFT_2B(taps[pB : (p+1)B) of channel c), cf. fir_p.c:482-498
-		const size_t n_taps = (size_t) filter_frames * fc;
-		double *d_taps = dev_alloc<double>(n_taps, false);
-		if (!d_taps) return -1;
-		CUDA_TRY(cudaMemcpyAsync(d_taps, h_taps.data(), n_taps * sizeof(double), cudaMemcpyHostToDevice, st), return -1);
-		const int nh = (fc == 1) ? 1 : n_sel;
-		for (int p = 0; p < P; ++p) {
-			FwdArgs a = {};
-			a.in = d_taps + (size_t) p * B * fc;
-			a.stride = fc; a.ch_map = nullptr; a.ch_mul = (fc == 1) ? 0 : 1;
-			a.valid = filter_frames - (long) p * B;
-			if (a.valid > B) a.valid = B;
-			a.spec = d_H; a.spec_ch_stride = (long) P * B; a.slot = p; a.tw = tw;
-			a.s0 = 0; a.s1 = nh;
-			if (launch_fwd(B, a, st)) return -1;
+		while (b * 2 <= hint && b < FIR_MAX_B) b *= 2;
+		B0 = b;
+		const long T = filter_frames;
+		// level plan (see the header comment)
+		n_levels = 0;
+		if (!multilevel || T <= 2L * B0 || B0 >= FIR_MAX_B) {
+			lv[0].B = B0; lv[0].tap0 = 0; lv[0].tap1 = T;
+			n_levels = 1;
 		}
-		// time-domain head taps h0[c][0:B)
-		std::vector<double> h0((size_t) nh * B, 0.0);
+		else {
+			lv[0].B = B0; lv[0].tap0 = 0; lv[0].tap1 = 2L * B0;
+			n_levels = 1;
+			long B = 2L * B0;
+			while (n_levels < FIR_MAX_LEVELS) {
+				FirLevel &L = lv[n_levels++];
+				L.B = (int) B; L.tap0 = B;
+				if (B >= FIR_MAX_B || T <= 2 * B || n_levels == FIR_MAX_LEVELS) { L.tap1 = T; break; }
+				L.tap1 = 2 * B;
+				B *= 2;
+			}
+		}
+		const int nh = (fc == 1) ? 1 : n_sel;
+		int Bmax = 0;
+		for (int l = 0; l < n_levels; ++l) {
+			FirLevel &L = lv[l];
+			L.P = (int) ((L.tap1 - L.tap0 + L.B - 1) / L.B);
+			L.tw = twiddles_2n(L.B);
+			L.ptw = twiddles_pass(L.B);
+			if (!L.tw || !L.ptw) return -1;
+			L.fdl = dev_alloc<double2>((size_t) n_sel * L.P * L.B);
+			L.H = dev_alloc<double2>((size_t) nh * L.P * L.B);
+			L.carry = dev_alloc<double>((size_t) n_sel * L.B);
+			if (l > 0) L.pend = dev_alloc<double>((size_t) n_sel * L.B);
+			if (!L.fdl || !L.H || !L.carry || (l > 0 && !L.pend)) return -1;
+			if (L.B > Bmax) Bmax = L.B;
+		}
+		hist_len = Bmax;
+		d_hist = dev_alloc<double>((size_t) n_sel * hist_len);
+		d_ytmp = dev_alloc<double>((size_t) n_sel * B0);
+		d_pre = dev_alloc<double>((size_t) n_sel * B0);
+		d_Y = dev_alloc<double2>((size_t) n_sel * Bmax);
+		d_h0 = dev_alloc<double>((size_t) nh * B0);
+		if (latency > 0) d_ring = dev_alloc<double>((size_t) latency * n_sel);
+		if (!d_hist || !d_ytmp || !d_pre || !d_Y || !d_h0 || (latency > 0 && !d_ring)) return -1;
+
+		// filter spectra H_l[c][p] = RFFT_2B(taps[tap0 + pB : tap0 + (p+1)B) of column c), cf. fir_p.c:482-498
+		double *d_taps = dev_alloc<double>((size_t) nh * T, false);
+		if (!d_taps) return -1;
+		CUDA_TRY(cudaMemcpyAsync(d_taps, h_taps.data(), (size_t) nh * T * sizeof(double), cudaMemcpyHostToDevice, st), return -1);
+		for (int l = 0; l < n_levels; ++l) {
+			FirLevel &L = lv[l];
+			for (int p = 0; p < L.P; ++p) {
+				FwdArgs a = {};
+				const long t0 = L.tap0 + (long) p * L.B;
+				a.in = d_taps + t0; a.ch_stride = T;
+				a.valid = L.tap1 - t0;
+				if (a.valid > L.B) a.valid = L.B;
+				a.spec = L.H; a.spec_ch_stride = (long) L.P * L.B; a.slot = p; a.tw = L.tw; a.ptw = L.ptw; a.n_ch = nh;
+				if (launch_fwd(L.B, a, st)) return -1;
+			}
+		}
+		// time-domain head taps h0[c][0:B0)
+		std::vector<double> h0((size_t) nh * B0, 0.0);
 		for (int c = 0; c < nh; ++c)
-			for (long i = 0; i < B && i < filter_frames; ++i)
-				h0[(size_t) c * B + i] = h_taps[(size_t) i * fc + c];
+			for (long i = 0; i < B0 && i < T; ++i) h0[(size_t) c * B0 + i] = h_taps[(size_t) c * T + i];
 		CUDA_TRY(cudaMemcpyAsync(d_h0, h0.data(), h0.size() * sizeof(double), cudaMemcpyHostToDevice, st), return -1);
 		CUDA_TRY(cudaStreamSynchronize(st), return -1);
 		dev_free(d_taps);
@@ -447,50 +666,77 @@ struct FirOp : Op {
 
 	void reset(cudaStream_t st) override
 	{
-		blk = 0; pos = 0; pre_valid = false; abs_frames = 0;
+		abs_pos = 0; pre_valid = false;
 		if (!planned) return;
-		cudaMemsetAsync(d_fdl, 0, (size_t) n_sel * P * B * sizeof(double2), st);
-		cudaMemsetAsync(d_carry, 0, (size_t) n_sel * B * sizeof(double), st);
-		cudaMemsetAsync(d_xcur, 0, (size_t) n_sel * B * sizeof(double), st);
+		for (int l = 0; l < n_levels; ++l) {
+			FirLevel &L = lv[l];
+			L.blk = 0;
+			cudaMemsetAsync(L.fdl, 0, (size_t) n_sel * L.P * L.B * sizeof(double2), st);
+			cudaMemsetAsync(L.carry, 0, (size_t) n_sel * L.B * sizeof(double), st);
+			if (L.pend) cudaMemsetAsync(L.pend, 0, (size_t) n_sel * L.B * sizeof(double), st);
+		}
+		cudaMemsetAsync(d_hist, 0, (size_t) n_sel * hist_len * sizeof(double), st);
 		if (d_ring) cudaMemsetAsync(d_ring, 0, (size_t) latency * n_sel * sizeof(double), st);
 	}
 
-	void mac(int p0, int p1, long slot_blk, cudaStream_t st)
+	void mac(FirLevel &L, int p0, int p1, long slot_blk, cudaStream_t st)
 	{
 		MacArgs m = {};
-		m.fdl = d_fdl; m.H = d_H; m.Y = d_Y; m.N = B; m.P = P;
-		m.slot0 = (int) (slot_blk % P); m.p0 = p0; m.p1 = p1;
-		m.h_ch_stride = (fc == 1) ? 0 : (long) P * B;
-		m.s0 = 0;
-		launch_mac(m, n_sel, fc == 1, st);
+		m.fdl = L.fdl; m.H = L.H; m.Y = d_Y; m.N = L.B; m.P = L.P;
+		m.slot0 = (int) (slot_blk % L.P); m.p0 = p0; m.p1 = p1;
+		m.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+		// the last level carries (almost) all the taps: it is the kernel the roofline line is about
+		launch_mac(m, n_sel, fc == 1, (&L == &lv[n_levels - 1]) ? "fir_mac" : "fir_mac_head", st);
 	}
 
-	// one whole aligned block: src/dst are interleaved with `stride`, channel offsets via ch_map
-	int fast_block(const double *src, long sstride, double *dst, long dstride, const int *dmap, long dmul, cudaStream_t st)
+	// block `L.blk` of level L is complete in the history ring: X into the FDL, S = MAC, IRFFT.
+	// flags/out as for k_fir_inv.
+	int level_block(FirLevel &L, double *out, long out_ch_stride, int inv_flags, cudaStream_t st)
 	{
 		FwdArgs f = {};
-		f.in = src; f.stride = sstride; f.ch_map = d_ch_map; f.ch_mul = 1; f.valid = B;
-		f.spec = d_fdl; f.spec_ch_stride = (long) P * B; f.slot = (int) (blk % P); f.tw = tw;
-		f.s0 = 0; f.s1 = n_sel;
-		if (launch_fwd(B, f, st)) return -1;
-		mac(0, P, blk, st);
+		f.in = d_hist + (L.blk * L.B) % hist_len; f.ch_stride = hist_len; f.valid = L.B;
+		f.spec = L.fdl; f.spec_ch_stride = (long) L.P * L.B; f.slot = (int) (L.blk % L.P); f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
+		if (launch_fwd(L.B, f, st)) return -1;
+		mac(L, 0, L.P, L.blk, st);
 		InvArgs v = {};
-		v.Y = d_Y; v.out = dst; v.stride = dstride; v.ch_map = dmap; v.ch_mul = dmul;
-		v.carry = d_carry; v.flags = INV_OUT | INV_UPDATE_CARRY; v.tw = tw; v.s0 = 0; v.s1 = n_sel;
-		if (launch_inv(B, v, st)) return -1;
-		++blk;
-		pre_valid = false;
+		v.Y = d_Y; v.out = out; v.out_ch_stride = out_ch_stride; v.carry = L.carry; v.flags = inv_flags; v.tw = L.tw; v.ptw = L.ptw; v.n_ch = n_sel;
+		if (launch_inv(L.B, v, st)) return -1;
+		++L.blk;
 		return 0;
+	}
+
+	// after level 0 finished a block: every larger level whose block just completed is advanced;
+	// its result becomes the pending contribution for its next block period
+	int advance_upper_levels(cudaStream_t st)
+	{
+		for (int l = 1; l < n_levels; ++l) {
+			FirLevel &L = lv[l];
+			if (abs_pos % L.B != 0) break;   // sizes double: if this one is not complete, none above is
+			if (level_block(L, L.pend, L.B, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
+		}
+		return 0;
+	}
+
+	PendArgs pend_args(long first_frame_abs) const
+	{
+		PendArgs p = {};
+		for (int l = 1; l < n_levels; ++l) {
+			p.buf[p.n] = lv[l].pend;
+			p.len[p.n] = lv[l].B;
+			p.off[p.n] = (int) (first_frame_abs % lv[l].B);
+			++p.n;
+		}
+		return p;
 	}
 
 	int ensure_pre(cudaStream_t st)
 	{
 		if (pre_valid) return 0;
-		mac(1, P, blk, st);   // R_blk: completed blocks only
+		FirLevel &L = lv[0];
+		mac(L, 1, L.P, L.blk, st);   // R: completed level-0 blocks only
 		InvArgs v = {};
-		v.Y = d_Y; v.out = d_pre; v.stride = 1; v.ch_map = nullptr; v.ch_mul = B;
-		v.carry = d_carry; v.flags = INV_OUT; v.tw = tw; v.s0 = 0; v.s1 = n_sel;
-		if (launch_inv(B, v, st)) return -1;
+		v.Y = d_Y; v.out = d_pre; v.out_ch_stride = B0; v.carry = L.carry; v.flags = INV_OUT; v.tw = L.tw; v.ptw = L.ptw; v.n_ch = n_sel;
+		if (launch_inv(B0, v, st)) return -1;
 		pre_valid = true;
 		return 0;
 	}
@@ -504,77 +750,74 @@ struct FirOp : Op {
 			CUDA_TRY(cudaMemcpyAsync(out, in, (size_t) frames * C * sizeof(double), cudaMemcpyDeviceToDevice, st), return -1);
 		if (n_sel == 0) return frames;
 
-		// where the convolution result goes: straight to `out`, or to a compact temp when a
-		// latency ring follows
+		// where the convolution result goes: straight to `out`, or to a compact temp when a latency ring follows
 		double *dst = out;
 		long dstride = C;
 		const int *dmap = d_ch_map;
 		if (latency > 0) {
-			if (ytmp_cap < frames) {
-				dev_free(d_ytmp);
-				d_ytmp = dev_alloc<double>((size_t) frames * n_sel, false);
-				if (!d_ytmp) return -1;
-				ytmp_cap = frames;
+			if (ltmp_cap < frames) {
+				dev_free(d_ltmp);
+				d_ltmp = dev_alloc<double>((size_t) frames * n_sel, false);
+				if (!d_ltmp) return -1;
+				ltmp_cap = frames;
 			}
-			dst = d_ytmp; dstride = n_sel; dmap = nullptr;
+			dst = d_ltmp; dstride = n_sel; dmap = nullptr;
 		}
+		const long abs0 = abs_pos;
+		FirLevel &L0 = lv[0];
+		const dim3 tgrid_full(ceil_div(B0, 32), ceil_div(n_sel, 32));
 
 		long done = 0;
 		while (done < frames) {
 			const double *src = in + done * C;
 			double *d = dst + done * dstride;
-			if (pos == 0 && frames - done >= B) {
-				if (fast_block(src, C, d, dstride, dmap, 1, st)) return -1;
-				done += B;
-				continue;
+			const int pos = (int) (abs_pos % B0);
+			const long blk_off = (abs_pos - pos) % hist_len;
+			const int seg = (int) ((frames - done < B0 - pos) ? frames - done : B0 - pos);
+			const PendArgs pend = pend_args(abs_pos);
+			// the new frames join the history ring
+			{
+				dim3 grid(ceil_div(seg, 32), ceil_div(n_sel, 32));
+				LAUNCH(k_fir_stash, grid, 256, 0, st, src, C, d_ch_map, d_hist, hist_len, blk_off + pos, seg, n_sel);
 			}
-			const int seg = (int) ((frames - done < B - pos) ? frames - done : B - pos);
-			if (ensure_pre(st)) return -1;
-			dim3 grid(ceil_div(seg, 128), n_sel);
-			LAUNCH(k_fir_stash, grid, 128, 0, st, src, C, d_ch_map, d_xcur, B, pos, seg, 0);
-			if (dmap) LAUNCH(k_fir_head, grid, 128, 0, st, d_xcur, d_pre, d_h0, (fc == 1) ? 0L : (long) B, d, dstride, dmap, B, pos, seg, 0);
-			else LAUNCH(k_fir_head, grid, 128, 0, st, d_xcur, d_pre, d_h0, (fc == 1) ? 0L : (long) B, d, dstride, d_iota(), B, pos, seg, 0);
-			pos += seg;
-			done += seg;
-			if (pos == B) {
-				// block complete: X_blk into the FDL, carry_blk = IRFFT(S_blk)[B:2B)
-				FwdArgs f = {};
-				f.in = d_xcur; f.stride = 1; f.ch_map = nullptr; f.ch_mul = B; f.valid = B;
-				f.spec = d_fdl; f.spec_ch_stride = (long) P * B; f.slot = (int) (blk % P); f.tw = tw;
-				f.s0 = 0; f.s1 = n_sel;
-				if (launch_fwd(B, f, st)) return -1;
-				mac(0, P, blk, st);
-				InvArgs v = {};
-				v.Y = d_Y; v.out = nullptr; v.stride = 0; v.ch_map = nullptr; v.ch_mul = 0;
-				v.carry = d_carry; v.flags = INV_UPDATE_CARRY; v.tw = tw; v.s0 = 0; v.s1 = n_sel;
-				if (launch_inv(B, v, st)) return -1;
-				++blk;
-				pos = 0;
+			if (pos == 0 && seg == B0) {
+				// fast path: one whole aligned block
+				if (L0.P <= 4) {
+					L0Args f = {};
+					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
+					f.fdl = L0.fdl; f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
+					f.P = L0.P; f.slot = (int) (L0.blk % L0.P);
+					f.out = d_ytmp; f.out_ch_stride = B0; f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
+					if (launch_level0(B0, f, st)) return -1;
+					++L0.blk;
+				}
+				else if (level_block(L0, d_ytmp, B0, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
+				LAUNCH(k_fir_unstash, tgrid_full, 256, 0, st, d_ytmp, (long) B0, pend, d, dstride, dmap, B0, n_sel);
 				pre_valid = false;
 			}
+			else {
+				if (ensure_pre(st)) return -1;
+				dim3 grid(ceil_div(seg, 128), n_sel);
+				LAUNCH(k_fir_head, grid, 128, 0, st, d_hist, hist_len, blk_off, d_pre, d_h0, (fc == 1) ? 0L : (long) B0, pend,
+				       d, dstride, dmap, B0, pos, seg);
+				if (pos + seg == B0) {
+					// block complete: X into the FDL, carry = IRFFT(S)[B:2B) (its first half has been emitted already)
+					if (level_block(L0, nullptr, 0, INV_UPDATE_CARRY, st)) return -1;
+					pre_valid = false;
+				}
+			}
+			abs_pos += seg;
+			done += seg;
+			if (abs_pos % B0 == 0 && advance_upper_levels(st)) return -1;
 		}
 
 		if (latency > 0) {
 			const long total = frames * n_sel;
-			LAUNCH(k_delay_read, ceil_div(total, 256), 256, 0, st, d_ytmp, (long) n_sel, d_ring, out, C, d_ch_map, n_sel, frames, latency, abs_frames);
+			LAUNCH(k_delay_read, ceil_div(total, 256), 256, 0, st, d_ltmp, (long) n_sel, d_ring, out, C, d_ch_map, n_sel, frames, latency, abs0);
 			const long cnt = (frames > latency) ? latency : frames;
-			LAUNCH(k_delay_write, ceil_div(cnt * n_sel, 256), 256, 0, st, d_ytmp, (long) n_sel, d_ring, n_sel, frames, latency, abs_frames);
+			LAUNCH(k_delay_write, ceil_div(cnt * n_sel, 256), 256, 0, st, d_ltmp, (long) n_sel, d_ring, n_sel, frames, latency, abs0);
 		}
-		abs_frames += frames;
 		return frames;
-	}
-
-	// identity map for the compact temp layout (head kernel wants a map)
-	int *d_iota_buf = nullptr;
-	const int *d_iota()
-	{
-		if (!d_iota_buf) {
-			std::vector<int> v(n_sel);
-			for (int i = 0; i < n_sel; ++i) v[i] = i;
-			d_iota_buf = dev_alloc<int>(n_sel, false);
-			cudaMemcpy(d_iota_buf, v.data(), n_sel * sizeof(int), cudaMemcpyHostToDevice);
-		}
-		return d_iota_buf;
 	}
 };
 
@@ -590,12 +833,17 @@ Op *make_fir_op(int slab_channels, int fs, const char *slab_selector, const doub
 	op->fc = (filter_channels == 1) ? 1 : op->n_sel;
 	op->filter_frames = filter_frames;
 	op->latency = latency;
+	const char *ml = getenv("DSP_B200_FIR_LEVELS");
+	op->multilevel = !(ml && ml[0] == '1' && ml[1] == '\0');
 	if (op->n_sel > 0) {
-		// gather this slab's columns of the filter: taps_cols[k] = column of the k-th selected channel
+		// gather this slab's columns of the filter, one contiguous row per column:
+		// taps_cols[k] = column of the k-th selected channel
 		op->h_taps.resize((size_t) filter_frames * op->fc);
-		for (long i = 0; i < filter_frames; ++i)
-			for (int k = 0; k < op->fc; ++k)
-				op->h_taps[(size_t) i * op->fc + k] = taps[(size_t) i * filter_channels + ((filter_channels == 1) ? 0 : taps_cols[k])];
+		for (int k = 0; k < op->fc; ++k) {
+			const int col = (filter_channels == 1) ? 0 : taps_cols[k];
+			for (long i = 0; i < filter_frames; ++i)
+				op->h_taps[(size_t) k * filter_frames + i] = taps[(size_t) i * filter_channels + col];
+		}
 		op->d_ch_map = dev_alloc<int>(op->n_sel, false);
 		if (!op->d_ch_map) return nullptr;
 		CUDA_TRY(cudaMemcpy(op->d_ch_map, op->h_ch_map.data(), op->n_sel * sizeof(int), cudaMemcpyHostToDevice), return nullptr);

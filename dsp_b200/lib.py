@@ -32,6 +32,7 @@ SIGNATURES = {
     "dspb200_chain_destroy": (None, [C.c_void_p]),
     "dspb200_chain_absorb": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dspb200_chain_n_ops": (C.c_int, [C.c_void_p]),
+    "dspb200_chain_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "dspb200_chain_n_shards": (C.c_int, [C.c_void_p]),
     "dspb200_chain_shard_info": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip]),
     "dspb200_chain_out_fs": (C.c_int, [C.c_void_p]),
@@ -182,6 +183,13 @@ class Chain:
     @property
     def n_ops(self):
         return lib().dspb200_chain_n_ops(self.h)
+
+    def describe(self):
+        """Operators of shard 0 with their plans (list of dicts)."""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        lib().dspb200_chain_describe(self.h, buf, len(buf))
+        return json.loads(buf.value.decode())
 
     @property
     def n_shards(self):

@@ -65,6 +65,8 @@ void dspb200_chain_destroy(dspb200_chain *c);
  * empty.  This is what an effect's merge() hook uses (effects_chain.c:605-641). */
 int  dspb200_chain_absorb(dspb200_chain *dest, dspb200_chain *src);
 int  dspb200_chain_n_ops(const dspb200_chain *c);
+/* JSON description of the operators of shard 0 (plans, partition levels); returns its length. */
+int  dspb200_chain_describe(const dspb200_chain *c, char *buf, size_t len);
 int  dspb200_chain_n_shards(const dspb200_chain *c);
 int  dspb200_chain_shard_info(const dspb200_chain *c, int shard, int *device, int *ch_begin, int *ch_count);
 int  dspb200_chain_out_fs(const dspb200_chain *c);
