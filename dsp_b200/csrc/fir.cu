@@ -132,18 +132,25 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_fwd(FwdArgs a)
 	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
 		double2 *X = a.spec + (long) s * a.spec_ch_stride + (long) a.slot * N;
-		for (int k = t; k <= N / 2; k += T) {
+		// every thread owns the 8 bin pairs (k, N-k), k = t + i T; thread 0 also owns k = 0 and k = N/2
+		double2 w[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) w[i] = __ldg(&a.tw[t + i * T]);
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int k = t + i * T;
 			if (k == 0) {
-				const double2 z0 = buf[0];
+				const double2 z0 = buf[0], zh = buf[spad(N / 2)];
 				X[0] = make_double2(z0.x + z0.y, z0.x - z0.y);
+				X[N / 2] = cconj(zh);   // E = Re z, O = Im z, w = -i
 			}
 			else {
 				const double2 zk = buf[spad(k)], zn = buf[spad(N - k)];
 				const double2 e = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
 				const double2 o = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
-				const double2 wo = cmul(__ldg(&a.tw[k]), o);
+				const double2 wo = cmul(w[i], o);
 				X[k] = cadd(e, wo);
-				if (k != N / 2) X[N - k] = cconj(csub(e, wo));
+				X[N - k] = cconj(csub(e, wo));
 			}
 		}
 	}
@@ -173,17 +180,26 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 
 	if (active) {
 		const double2 *Y = a.Y + (long) s * N;
-		for (int k = t; k <= N / 2; k += T) {
+		double2 yk[8], yn[8], w[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int k = t + i * T;
+			yk[i] = Y[k];
+			yn[i] = Y[(k == 0) ? N / 2 : N - k];
+			w[i] = __ldg(&a.tw[k]);
+		}
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int k = t + i * T;
 			if (k == 0) {
-				const double2 y0 = Y[0];
-				// Z[0] = E0 + i O0, stored conjugated
-				buf[0] = make_double2(0.5 * (y0.x + y0.y), -0.5 * (y0.x - y0.y));
+				// Z[0] = E0 + i O0 from the packed (DC, Nyquist) pair; Z[N/2] = conj(Y[N/2]); both stored conjugated
+				buf[0] = make_double2(0.5 * (yk[i].x + yk[i].y), -0.5 * (yk[i].x - yk[i].y));
+				buf[spad(N / 2)] = yn[i];
 			}
 			else {
-				const double2 xk = Y[k], xn = Y[N - k];
-				const double2 e = make_double2(0.5 * (xk.x + xn.x), 0.5 * (xk.y - xn.y));
-				const double2 d = make_double2(0.5 * (xk.x - xn.x), 0.5 * (xk.y + xn.y));
-				const double2 o = cmul(cconj(__ldg(&a.tw[k])), d);
+				const double2 e = make_double2(0.5 * (yk[i].x + yn[i].x), 0.5 * (yk[i].y - yn[i].y));
+				const double2 d = make_double2(0.5 * (yk[i].x - yn[i].x), 0.5 * (yk[i].y + yn[i].y));
+				const double2 o = cmul(cconj(w[i]), d);
 				// Z[k] = E + iO, Z[N-k] = conj(E) + i conj(O); store conj(Z)
 				buf[spad(k)] = make_double2(e.x - o.y, -(e.y + o.x));
 				buf[spad(N - k)] = make_double2(e.x + o.y, -(o.x - e.y));
@@ -196,18 +212,22 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 		const double scale = 1.0 / N;
 		double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
 		double2 *out = reinterpret_cast<double2 *>(a.out + (long) s * a.out_ch_stride);
-		for (int n = t; n < N / 2; n += T) {
+		double2 c[8];
+		if (a.flags & INV_OUT) {
+#pragma unroll
+			for (int i = 0; i < 8; ++i) c[i] = carry[t + i * T];
+		}
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int n = t + i * T;
 			const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
-			if (a.flags & INV_OUT) {
-				const double2 c = carry[n];
-				out[n] = make_double2(fma(lo.x, scale, c.x), fma(-lo.y, scale, c.y));
-			}
+			if (a.flags & INV_OUT) out[n] = make_double2(fma(lo.x, scale, c[i].x), fma(-lo.y, scale, c[i].y));
 			if (a.flags & INV_UPDATE_CARRY) carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 		}
 	}
 }
 
-// Level 0 in one kernel when it has few partitions (P <= 4; P = 2 whenever larger levels exist):
+// Level 0 in one kernel when it has at most two partitions (P = 2 whenever larger levels exist):
 // forward transform of the new block, its spectrum into the FDL, S = X_j H_0 + sum_{p>=1} X_{j-p} H_p
 // formed by the thread that owns the bin pair (k, N-k) straight from registers, inverse transform in
 // the same shared-memory buffer, overlap-add epilogue.  One launch instead of three and no spectrum
@@ -231,7 +251,7 @@ __device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 h)
 	return make_double2(fma(x.x, h.x, fma(-x.y, h.y, acc.x)), fma(x.x, h.y, fma(x.y, h.x, acc.y)));
 }
 
-template <int N>
+template <int N, int P>
 __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 {
 	extern __shared__ double2 smem[];
@@ -243,52 +263,76 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 
 	if (active) {
 		const double2 *x = reinterpret_cast<const double2 *>(a.in + (long) s * a.in_ch_stride);
-		for (int n = t; n < N / 2; n += T) {
-			buf[spad(n)] = x[n];
-			buf[spad(n + N / 2)] = make_double2(0.0, 0.0);
+		double2 v[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) v[i] = x[t + i * T];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			buf[spad(t + i * T)] = v[i];
+			buf[spad(t + i * T + N / 2)] = make_double2(0.0, 0.0);
 		}
 	}
 	__syncthreads();
 	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
-		double2 *fdl = a.fdl + (long) s * a.P * N;
+		double2 *fdl = a.fdl + (long) s * P * N;
 		const double2 *H = a.H + (long) s * a.h_ch_stride;
 		double2 *X = fdl + (long) a.slot * N;
-		for (int k = t; k <= N / 2; k += T) {
+		double2 w[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) w[i] = __ldg(&a.tw[t + i * T]);
+		// (1) real split: X[k], X[N-k] to the FDL and, in place of Z, to shared memory.
+		//     Thread t owns the pairs k = t + i T; thread 0 also owns k = 0 (packed DC/Nyquist) and k = N/2.
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int k = t + i * T;
 			if (k == 0) {
-				const double2 z0 = buf[0];
-				const double2 x0 = make_double2(z0.x + z0.y, z0.x - z0.y);
-				X[0] = x0;
-				const double2 h0 = H[0];
-				double2 S = make_double2(x0.x * h0.x, x0.y * h0.y);   // packed: DC and Nyquist are separate real products
-				for (int p = 1; p < a.P; ++p) {
-					const int sl = (a.slot - p < 0) ? a.slot - p + a.P : a.slot - p;
-					const double2 xp = fdl[(long) sl * N], hp = H[(long) p * N];
-					S.x = fma(xp.x, hp.x, S.x);
-					S.y = fma(xp.y, hp.y, S.y);
-				}
-				buf[0] = make_double2(0.5 * (S.x + S.y), -0.5 * (S.x - S.y));
+				const double2 z0 = buf[0], zh = buf[spad(N / 2)];
+				const double2 x0 = make_double2(z0.x + z0.y, z0.x - z0.y), xh = cconj(zh);
+				X[0] = x0; X[N / 2] = xh;
+				buf[0] = x0; buf[spad(N / 2)] = xh;
 			}
 			else {
-				const int n = N - k;
-				const double2 zk = buf[spad(k)], zn = buf[spad(n)];
+				const double2 zk = buf[spad(k)], zn = buf[spad(N - k)];
 				const double2 e0 = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
 				const double2 o0 = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
-				const double2 w = __ldg(&a.tw[k]);
-				const double2 wo = cmul(w, o0);
+				const double2 wo = cmul(w[i], o0);
 				const double2 xk = cadd(e0, wo), xn = cconj(csub(e0, wo));
-				X[k] = xk;
-				if (k != N / 2) X[n] = xn;
-				double2 Sk = cmul(xk, H[k]), Sn = cmul(xn, H[n]);
-				for (int p = 1; p < a.P; ++p) {
-					const int sl = (a.slot - p < 0) ? a.slot - p + a.P : a.slot - p;
-					Sk = cmac(Sk, fdl[(long) sl * N + k], H[(long) p * N + k]);
-					Sn = cmac(Sn, fdl[(long) sl * N + n], H[(long) p * N + n]);
-				}
-				// inverse merge of (S[k], S[N-k]) -> conj(Z[k]), conj(Z[N-k])
+				X[k] = xk; X[N - k] = xn;
+				buf[spad(k)] = xk; buf[spad(N - k)] = xn;
+			}
+		}
+		// (2) S = X_j H_0 + sum_{p>=1} X_{j-p} H_p for the owned bins (no global stores in this loop, so the
+		//     loads of all iterations can be in flight together), then the inverse merge into shared memory
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int k = t + i * T;
+			const int n = (k == 0) ? N / 2 : N - k;
+			double2 Sk, Sn;
+			{
+				const double2 xk = buf[spad(k)], xn = buf[spad(n)];
+				const double2 hk = H[k], hn = H[n];
+				if (k == 0) Sk = make_double2(xk.x * hk.x, xk.y * hk.y);   // packed bin: two real products
+				else Sk = cmul(xk, hk);
+				Sn = cmul(xn, hn);
+			}
+#pragma unroll
+			for (int p = 1; p < P; ++p) {
+				const int sl = (a.slot - p < 0) ? a.slot - p + P : a.slot - p;
+				const double2 xk = fdl[(long) sl * N + k], xn = fdl[(long) sl * N + n];
+				const double2 hk = H[(long) p * N + k], hn = H[(long) p * N + n];
+				if (k == 0) { Sk.x = fma(xk.x, hk.x, Sk.x); Sk.y = fma(xk.y, hk.y, Sk.y); }
+				else Sk = cmac(Sk, xk, hk);
+				Sn = cmac(Sn, xn, hn);
+			}
+			if (k == 0) {
+				buf[0] = make_double2(0.5 * (Sk.x + Sk.y), -0.5 * (Sk.x - Sk.y));
+				buf[spad(N / 2)] = Sn;   // conj(Z[N/2]) = S[N/2]
+			}
+			else {
 				const double2 e = make_double2(0.5 * (Sk.x + Sn.x), 0.5 * (Sk.y - Sn.y));
 				const double2 d = make_double2(0.5 * (Sk.x - Sn.x), 0.5 * (Sk.y + Sn.y));
-				const double2 o = cmul(cconj(w), d);
+				const double2 o = cmul(cconj(w[i]), d);
 				buf[spad(k)] = make_double2(e.x - o.y, -(e.y + o.x));
 				buf[spad(n)] = make_double2(e.x + o.y, -(o.x - e.y));
 			}
@@ -300,10 +344,14 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 		const double scale = 1.0 / N;
 		double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
 		double2 *out = reinterpret_cast<double2 *>(a.out + (long) s * a.out_ch_stride);
-		for (int n = t; n < N / 2; n += T) {
+		double2 c[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) c[i] = carry[t + i * T];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int n = t + i * T;
 			const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
-			const double2 c = carry[n];
-			out[n] = make_double2(fma(lo.x, scale, c.x), fma(-lo.y, scale, c.y));
+			out[n] = make_double2(fma(lo.x, scale, c[i].x), fma(-lo.y, scale, c[i].y));
 			carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 		}
 	}
@@ -428,7 +476,8 @@ static int configure_n()
 	if (!configured[dev & 63].load()) {
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_fwd<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_inv<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
-		CUDA_TRY(cudaFuncSetAttribute(k_fir_level0<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
+		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
+		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		configured[dev & 63].store(1);
 	}
 	return 0;
@@ -460,7 +509,8 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 	if (configure_n<N>()) return -1;
 	if (a.n_ch <= 0) return 0;
 	ProfScope prof("fir_level0", st);
-	LAUNCH(k_fir_level0<N>, ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	if (a.P == 1) LAUNCH((k_fir_level0<N, 1>), ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	else LAUNCH((k_fir_level0<N, 2>), ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
 	return 0;
 }
 
@@ -782,7 +832,7 @@ struct FirOp : Op {
 			}
 			if (pos == 0 && seg == B0) {
 				// fast path: one whole aligned block
-				if (L0.P <= 4) {
+				if (L0.P <= 2) {
 					L0Args f = {};
 					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
 					f.fdl = L0.fdl; f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
