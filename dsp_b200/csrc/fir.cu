@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 struct L0Args {
 	const double *in;        // per-channel contiguous block (history ring)
 	long in_ch_stride;
-	double2 *fdl;            // [s][P][N]
-	const double2 *H;        // [s or 0][P][N]
+	double2 *fdl;            // [s][fdl_ch_stride], rows of N
+	long fdl_ch_stride;      // rows per channel * N
+	int fdl_rows;            // rows per channel (slot arithmetic)
+	const double2 *H;        // [s or 0][rows][N]
 	long h_ch_stride;
 	int P, slot;
 	double *out;             // [s][out_ch_stride]: first half + carry
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 	__syncthreads();
 	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
-		double2 *fdl = a.fdl + (long) s * P * N;
+		double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride;
 		const double2 *H = a.H + (long) s * a.h_ch_stride;
 		double2 *X = fdl + (long) a.slot * N;
 		double2 w[8];
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 			}
 #pragma unroll
 			for (int p = 1; p < P; ++p) {
-				const int sl = (a.slot - p < 0) ? a.slot - p + P : a.slot - p;
+				const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
 				const double2 xk = fdl[(long) sl * N + k], xn = fdl[(long) sl * N + n];
 				const double2 hk = H[(long) p * N + k], hn = H[(long) p * N + n];
 				if (k == 0) { Sk.x = fma(xk.x, hk.x, Sk.x); Sk.y = fma(xk.y, hk.y, Sk.y); }
@@ -587,9 +589,15 @@ struct FirLevel {
 	const double2 *tw = nullptr, *ptw = nullptr;
 	double2 *fdl = nullptr, *H = nullptr;
 	double *carry = nullptr, *pend = nullptr;
+	// last level only: partitions p >= 1 ("tail") run on a side stream one block period ahead
+	double *carry_tail = nullptr, *pend_tail[2] = { nullptr, nullptr };
 	long blk = 0;                 // completed blocks of this level
 
-	void free_all() { dev_free(fdl); dev_free(H); dev_free(carry); dev_free(pend); }
+	void free_all()
+	{
+		dev_free(fdl); dev_free(H); dev_free(carry); dev_free(pend);
+		dev_free(carry_tail); dev_free(pend_tail[0]); dev_free(pend_tail[1]);
+	}
 };
 
 struct FirOp : Op {
@@ -612,7 +620,13 @@ struct FirOp : Op {
 	int *d_ch_map = nullptr;
 	double *d_hist = nullptr, *d_ytmp = nullptr, *d_pre = nullptr, *d_h0 = nullptr;
 	double2 *d_Y = nullptr;              // [n_sel][max B]
+	double2 *d_Y_side = nullptr;         // same, for the side stream
 	double *d_ring = nullptr, *d_ltmp = nullptr;
+	// side stream: the last level's tail (MAC over p >= 1 + inverse) overlaps the main stream's next period
+	cudaStream_t side = nullptr;
+	cudaEvent_t ev_main = nullptr, ev_urgent = nullptr, ev_side[2] = { nullptr, nullptr };
+	long waited_period = -1;
+	bool urgent_pending = false;
 	long ltmp_cap = 0;
 	long abs_pos = 0;                    // frames consumed so far (level-0 block = abs_pos / B0, offset = abs_pos % B0)
 	bool pre_valid = false;
@@ -632,7 +646,16 @@ struct FirOp : Op {
 
 	~FirOp() override
 	{
+		if (side) {
+			cudaStreamSynchronize(side);
+			cudaStreamDestroy(side);
+		}
+		if (ev_main) cudaEventDestroy(ev_main);
+		if (ev_urgent) cudaEventDestroy(ev_urgent);
+		for (cudaEvent_t e : ev_side)
+			if (e) cudaEventDestroy(e);
 		for (int l = 0; l < n_levels; ++l) lv[l].free_all();
+		dev_free(d_Y_side);
 		dev_free(d_ch_map); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp);
 	}
@@ -674,9 +697,27 @@ struct FirOp : Op {
 			L.carry = dev_alloc<double>((size_t) n_sel * L.B);
 			if (l > 0) L.pend = dev_alloc<double>((size_t) n_sel * L.B);
 			if (!L.fdl || !L.H || !L.carry || (l > 0 && !L.pend)) return -1;
+			if (l > 0 && !side) {
+				int lo = 0, hi = 0;
+				cudaDeviceGetStreamPriorityRange(&lo, &hi);
+				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo), return -1);
+				CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming), return -1);
+				CUDA_TRY(cudaEventCreateWithFlags(&ev_urgent, cudaEventDisableTiming), return -1);
+				CUDA_TRY(cudaEventCreateWithFlags(&ev_side[0], cudaEventDisableTiming), return -1);
+				CUDA_TRY(cudaEventCreateWithFlags(&ev_side[1], cudaEventDisableTiming), return -1);
+			}
+			if (l > 0 && l == n_levels - 1 && L.P > 1) {
+				L.carry_tail = dev_alloc<double>((size_t) n_sel * L.B);
+				L.pend_tail[0] = dev_alloc<double>((size_t) n_sel * L.B);
+				L.pend_tail[1] = dev_alloc<double>((size_t) n_sel * L.B);
+				d_Y_side = dev_alloc<double2>((size_t) n_sel * L.B);
+				if (!L.carry_tail || !L.pend_tail[0] || !L.pend_tail[1] || !d_Y_side) return -1;
+			}
 			if (L.B > Bmax) Bmax = L.B;
 		}
-		hist_len = Bmax;
+		// upper levels read their block from the ring on the side stream while the next block is already
+		// being stashed: keep two of the largest blocks
+		hist_len = (n_levels > 1) ? 2L * Bmax : Bmax;
 		d_hist = dev_alloc<double>((size_t) n_sel * hist_len);
 		d_ytmp = dev_alloc<double>((size_t) n_sel * B0);
 		d_pre = dev_alloc<double>((size_t) n_sel * B0);
@@ -716,11 +757,17 @@ struct FirOp : Op {
 
 	void reset(cudaStream_t st) override
 	{
-		abs_pos = 0; pre_valid = false;
+		abs_pos = 0; pre_valid = false; waited_period = -1; urgent_pending = false;
 		if (!planned) return;
+		if (side) cudaStreamSynchronize(side);
 		for (int l = 0; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			L.blk = 0;
+			if (L.carry_tail) {
+				cudaMemsetAsync(L.carry_tail, 0, (size_t) n_sel * L.B * sizeof(double), st);
+				cudaMemsetAsync(L.pend_tail[0], 0, (size_t) n_sel * L.B * sizeof(double), st);
+				cudaMemsetAsync(L.pend_tail[1], 0, (size_t) n_sel * L.B * sizeof(double), st);
+			}
 			cudaMemsetAsync(L.fdl, 0, (size_t) n_sel * L.P * L.B * sizeof(double2), st);
 			cudaMemsetAsync(L.carry, 0, (size_t) n_sel * L.B * sizeof(double), st);
 			if (L.pend) cudaMemsetAsync(L.pend, 0, (size_t) n_sel * L.B * sizeof(double), st);
@@ -729,10 +776,10 @@ struct FirOp : Op {
 		if (d_ring) cudaMemsetAsync(d_ring, 0, (size_t) latency * n_sel * sizeof(double), st);
 	}
 
-	void mac(FirLevel &L, int p0, int p1, long slot_blk, cudaStream_t st)
+	void mac(FirLevel &L, int p0, int p1, long slot_blk, cudaStream_t st, double2 *Y = nullptr)
 	{
 		MacArgs m = {};
-		m.fdl = L.fdl; m.H = L.H; m.Y = d_Y; m.N = L.B; m.P = L.P;
+		m.fdl = L.fdl; m.H = L.H; m.Y = Y ? Y : d_Y; m.N = L.B; m.P = L.P;
 		m.slot0 = (int) (slot_blk % L.P); m.p0 = p0; m.p1 = p1;
 		m.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 		// the last level carries (almost) all the taps: it is the kernel the roofline line is about
@@ -755,28 +802,83 @@ struct FirOp : Op {
 		return 0;
 	}
 
-	// after level 0 finished a block: every larger level whose block just completed is advanced;
-	// its result becomes the pending contribution for its next block period
+	// After level 0 finished a block: every larger level whose block just completed is advanced -- on the
+	// SIDE stream, so that the caller's stream (and, in host mode, the D2H of the block just produced and
+	// the H2D of the next one) is not held up by work whose result is only due later:
+	//   - partition 0 of the level is due in the very next block period: fused kernel (spectrum into the
+	//     level's FDL, result into `pend`), `ev_urgent` tells the main stream when it is there;
+	//   - the last level's partitions p >= 1 only involve blocks that were complete one period ago:
+	//     R_{q+1} = sum_{p>=1} X_{q+1-p} H_p is launched now (block q just completed) and consumed in
+	//     period q+2, so the HBM-streaming MAC has a whole period to overlap with the FFT kernels.
 	int advance_upper_levels(cudaStream_t st)
 	{
+		bool any = false;
 		for (int l = 1; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			if (abs_pos % L.B != 0) break;   // sizes double: if this one is not complete, none above is
-			if (level_block(L, L.pend, L.B, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
+			if (!any) {
+				CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
+				CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
+				any = true;
+			}
+			L0Args f = {};
+			f.in = d_hist + (L.blk * L.B) % hist_len; f.in_ch_stride = hist_len;
+			f.fdl = L.fdl; f.fdl_ch_stride = (long) L.P * L.B; f.fdl_rows = L.P;
+			f.H = L.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+			f.P = 1; f.slot = (int) (L.blk % L.P);
+			f.out = L.pend; f.out_ch_stride = L.B; f.carry = L.carry; f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
+			if (launch_level0(L.B, f, side)) return -1;
+			++L.blk;
+		}
+		if (!any) return 0;
+		CUDA_TRY(cudaEventRecord(ev_urgent, side), return -1);
+		urgent_pending = true;
+		FirLevel &L = lv[n_levels - 1];
+		if (L.carry_tail && abs_pos % L.B == 0) {
+			const long q1 = L.blk;   // R_{q+1}, q = the block that just completed
+			mac(L, 1, L.P, q1, side, d_Y_side);
+			InvArgs v = {};
+			v.Y = d_Y_side; v.out = L.pend_tail[q1 & 1]; v.out_ch_stride = L.B; v.carry = L.carry_tail;
+			v.flags = INV_OUT | INV_UPDATE_CARRY; v.tw = L.tw; v.ptw = L.ptw; v.n_ch = n_sel;
+			if (launch_inv(L.B, v, side)) return -1;
+			CUDA_TRY(cudaEventRecord(ev_side[q1 & 1], side), return -1);
 		}
 		return 0;
 	}
 
+	// What the unstash / head kernels add on top of level 0 for the frames starting at `first_frame_abs`.
+	// In period q of the last level the tail result R_{q-1} is consumed (launched at the end of period
+	// q-2, see advance_upper_levels); side_wait() makes `st` wait for it, once per period, right before
+	// the first kernel that reads it.
 	PendArgs pend_args(long first_frame_abs) const
 	{
 		PendArgs p = {};
 		for (int l = 1; l < n_levels; ++l) {
-			p.buf[p.n] = lv[l].pend;
-			p.len[p.n] = lv[l].B;
-			p.off[p.n] = (int) (first_frame_abs % lv[l].B);
+			const FirLevel &L = lv[l];
+			const int off = (int) (first_frame_abs % L.B);
+			p.buf[p.n] = L.pend; p.len[p.n] = L.B; p.off[p.n] = off;
 			++p.n;
+			if (L.carry_tail) {
+				const long q = first_frame_abs / L.B;
+				p.buf[p.n] = L.pend_tail[(q + 1) & 1]; p.len[p.n] = L.B; p.off[p.n] = off;   // (q - 1) & 1
+				++p.n;
+			}
 		}
 		return p;
+	}
+
+	void side_wait(long first_frame_abs, cudaStream_t st)
+	{
+		if (urgent_pending) {
+			cudaStreamWaitEvent(st, ev_urgent, 0);
+			urgent_pending = false;
+		}
+		const FirLevel &L = lv[n_levels - 1];
+		if (!L.carry_tail) return;
+		const long q = first_frame_abs / L.B;
+		if (q == waited_period) return;
+		if (q >= 2) cudaStreamWaitEvent(st, ev_side[(q + 1) & 1], 0);
+		waited_period = q;
 	}
 
 	int ensure_pre(cudaStream_t st)
@@ -835,19 +937,22 @@ struct FirOp : Op {
 				if (L0.P <= 2) {
 					L0Args f = {};
 					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
-					f.fdl = L0.fdl; f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
+					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.P * B0; f.fdl_rows = L0.P;
+					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
 					f.P = L0.P; f.slot = (int) (L0.blk % L0.P);
 					f.out = d_ytmp; f.out_ch_stride = B0; f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
 					if (launch_level0(B0, f, st)) return -1;
 					++L0.blk;
 				}
 				else if (level_block(L0, d_ytmp, B0, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
+				side_wait(abs_pos, st);
 				LAUNCH(k_fir_unstash, tgrid_full, 256, 0, st, d_ytmp, (long) B0, pend, d, dstride, dmap, B0, n_sel);
 				pre_valid = false;
 			}
 			else {
 				if (ensure_pre(st)) return -1;
 				dim3 grid(ceil_div(seg, 128), n_sel);
+				side_wait(abs_pos, st);
 				LAUNCH(k_fir_head, grid, 128, 0, st, d_hist, hist_len, blk_off, d_pre, d_h0, (fc == 1) ? 0L : (long) B0, pend,
 				       d, dstride, dmap, B0, pos, seg);
 				if (pos + seg == B0) {
