@@ -296,6 +296,18 @@ void *dspb200_host_alloc(size_t bytes)
 	return p;
 }
 
+void *dspb200_host_alloc_wc(size_t bytes)
+{
+	// write-combined: faster for the GPU to read over PCIe, slow for the CPU to read back -- input buffers only
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) {
+		set_error("cudaHostAlloc(%zu, write-combined) failed", bytes);
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
 void dspb200_host_free(void *p)
 {
 	if (p) cudaFreeHost(p);

@@ -110,7 +110,7 @@ __global__ void k_rs_sinc_dft(const double *sinc, int m_os, int K, double2 *S)
 }
 
 // G[ph][t] = g(ph + t n)
-__global__ void k_rs_table(const double2 *S, int K, int n, int in_len, double *G)
+__global__ void k_rs_table(const double2 *S, int K, int n, int in_len, double *G, int g_stride, int pad)
 {
 	const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= (long) n * in_len) return;
@@ -126,42 +126,82 @@ __global__ void k_rs_table(const double2 *S, int K, int n, int in_len, double *G
 		const double term = s.x * cs - s.y * sn;
 		acc += (k == K) ? 0.5 * term : term;
 	}
-	G[idx] = (S[0].x + 2.0 * acc) / (2.0 * in_len);
+	G[(long) ph * g_stride + pad + t] = (S[0].x + 2.0 * acc) / (2.0 * in_len);   // rows are zero-padded by `pad` on both sides
 }
 
-// out[q][c] = sum_t G[(m d) % n][t] * x[(m d) / n - t][c],  m = m0 + q;  x lives in a ring of rows
-__global__ void __launch_bounds__(256) k_rs_poly(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
-                                                 int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
+// out[q][c] = sum_t G[(m d) % n][t] * x[(m d) / n - t][c],  m = m0 + q;  x lives in a ring of rows.
+// Register-blocked: a warp produces R consecutive output frames for 32*CH channels (lane = CH adjacent
+// channels).  It walks the input rows i downwards once; every row is loaded once (CH doubles per lane,
+// coalesced) and feeds all R outputs, each with its own tap G[ph_r][i_hi_r - i] (warp-uniform load).
+// Tap rows are zero-padded by `pad` on both sides, so the ragged ends of the R tap windows need no
+// branches.  2 R CH flops per (1 + R) loads.
+template <int R, int CH>
+__global__ void __launch_bounds__(128) k_rs_poly(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
+                                                 int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int c = blockIdx.y * 32 + lane;
-	const long q = (long) blockIdx.x * 8 + warp;
-	if (q >= n_out) return;
-	const long md = (m0 + q) * d;
-	const long i_hi = md / n;
-	const int ph = (int) (md - i_hi * n);
-	const double *g = G + (long) ph * in_len;
-	const int taps = (int) ((i_hi + 1 < in_len) ? i_hi + 1 : in_len);   // rows before the stream start are zero
-	long r = i_hi % ring_len;
-	const bool act = c < C;
-	const double *col = ring + (act ? c : 0);
-	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-	int t = 0;
-	for (; t + 4 <= taps; t += 4) {
-		const long r0 = r, r1 = (r0 == 0) ? ring_len - 1 : r0 - 1, r2 = (r1 == 0) ? ring_len - 1 : r1 - 1, r3 = (r2 == 0) ? ring_len - 1 : r2 - 1;
-		const double x0 = col[r0 * C], x1 = col[r1 * C], x2 = col[r2 * C], x3 = col[r3 * C];
-		a0 = fma(__ldg(&g[t]), x0, a0);
-		a1 = fma(__ldg(&g[t + 1]), x1, a1);
-		a2 = fma(__ldg(&g[t + 2]), x2, a2);
-		a3 = fma(__ldg(&g[t + 3]), x3, a3);
-		r = (r3 == 0) ? ring_len - 1 : r3 - 1;
+	const int c0 = (blockIdx.y * 32 + lane) * CH;
+	const long q0 = ((long) blockIdx.x * 4 + warp) * R;
+	if (q0 >= n_out) return;
+	long ih[R];
+	const double *g[R];
+#pragma unroll
+	for (int r = 0; r < R; ++r) {
+		long q = q0 + r;
+		if (q >= n_out) q = n_out - 1;   // duplicates the last frame's work; not stored
+		const long md = (m0 + q) * d;
+		ih[r] = md / n;
+		g[r] = G + (md - ih[r] * n) * g_stride + pad;
 	}
-	for (; t < taps; ++t) {
-		a0 = fma(__ldg(&g[t]), col[r * C], a0);
-		r = (r == 0) ? ring_len - 1 : r - 1;
+	const long i_top = ih[R - 1];
+	long i_bot = ih[0] - in_len + 1;
+	if (i_bot < 0) i_bot = 0;   // rows before the stream start are zero
+#pragma unroll
+	for (int r = 0; r < R; ++r) g[r] += ih[r] - i_top;   // tap index of row i_top (<= 0, inside the left pad)
+	double acc[R][CH];
+#pragma unroll
+	for (int r = 0; r < R; ++r)
+#pragma unroll
+		for (int h = 0; h < CH; ++h) acc[r][h] = 0.0;
+	const bool act = c0 < C;
+	long row = i_top % ring_len;
+	const double *col = ring + (act ? c0 : 0);
+	for (long i = i_top; i >= i_bot; --i) {
+		double x[CH];
+		const double *p = col + row * C;
+		if (CH == 4) {
+			const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+			x[0] = a.x; x[1] = a.y; x[2 % CH] = b.x; x[3 % CH] = b.y;
+		}
+		else if (CH == 2) {
+			const double2 a = *reinterpret_cast<const double2 *>(p);
+			x[0] = a.x; x[1 % CH] = a.y;
+		}
+		else x[0] = p[0];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const double w = __ldg(g[r]);
+			++g[r];
+#pragma unroll
+			for (int h = 0; h < CH; ++h) acc[r][h] = fma(w, x[h], acc[r][h]);
+		}
+		row = (row == 0) ? ring_len - 1 : row - 1;
 	}
-	if (act) out[q * C + c] = (a0 + a1) + (a2 + a3);
+	if (!act) return;
+#pragma unroll
+	for (int r = 0; r < R; ++r) {
+		if (q0 + r >= n_out) break;
+		double *o = out + (q0 + r) * C + c0;
+		if (CH == 4) {
+			*reinterpret_cast<double2 *>(o) = make_double2(acc[r][0], acc[r][1 % CH]);
+			*reinterpret_cast<double2 *>(o + 2) = make_double2(acc[r][2 % CH], acc[r][3 % CH]);
+		}
+		else if (CH == 2) *reinterpret_cast<double2 *>(o) = make_double2(acc[r][0], acc[r][1 % CH]);
+		else o[0] = acc[r][0];
+	}
 }
+
+constexpr int RS_R = 8;   // output frames per warp
 
 // move the live rows of the input ring into a bigger ring (absolute frame a lives at a % len)
 __global__ void k_rs_ring_grow(const double *old_ring, long old_len, double *new_ring, long new_len, int C, long a0, long rows)
@@ -176,6 +216,7 @@ __global__ void k_rs_ring_grow(const double *old_ring, long old_len, double *new
 struct ResampleOp : Op {
 	ResampleParams p;
 	double *d_G = nullptr, *d_ring = nullptr;
+	int g_stride = 0, g_pad = 0;         // tap rows: [pad zeros | in_len taps | pad zeros]
 	long ring_len = 0;
 	// resample.c:39-50 bookkeeping (integers only; the sample data lives in the ring)
 	long total_in = 0;          // frames appended since reset
@@ -265,9 +306,24 @@ struct ResampleOp : Op {
 		}
 		const long first_m = emit_pos;   // emission is one contiguous raw range per call
 		if (oframes > 0) {
-			dim3 grid(ceil_div(oframes, 8), ceil_div(C, 32));
 			ProfScope prof("resample", st);
-			LAUNCH(k_rs_poly, grid, 256, 0, st, d_ring, ring_len, C, d_G, p.n, p.d, p.in_len, first_m, oframes, out);
+			// pick the register tile so that the grid still fills the chip: wide tiles (8 frames x 4 channels
+			// per lane) have the best flop/load ratio, narrow ones more warps
+			const long warps84 = (long) ceil_div(oframes, 8) * ceil_div(C, 128);
+			const long warps82 = (long) ceil_div(oframes, 8) * ceil_div(C, 64);
+			const long want = 148L * 24;
+			if (C % 4 == 0 && warps84 >= want) {
+				LAUNCH((k_rs_poly<8, 4>), dim3(ceil_div(oframes, 32), ceil_div(C, 128)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+			}
+			else if (C % 2 == 0 && warps82 >= want) {
+				LAUNCH((k_rs_poly<8, 2>), dim3(ceil_div(oframes, 32), ceil_div(C, 64)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+			}
+			else if (C % 2 == 0) {
+				LAUNCH((k_rs_poly<4, 2>), dim3(ceil_div(oframes, 16), ceil_div(C, 64)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+			}
+			else {
+				LAUNCH((k_rs_poly<4, 1>), dim3(ceil_div(oframes, 16), ceil_div(C, 32)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+			}
 			emit_pos += oframes;
 		}
 		return oframes;
@@ -314,11 +370,14 @@ Op *make_resample_op(int slab_channels, int fs_in, int fs_out, double bandwidth,
 	}
 	double *d_sinc = dev_alloc<double>(sinc.size(), false);
 	double2 *d_S = dev_alloc<double2>((size_t) p.sinc_len + 1, false);
-	op->d_G = dev_alloc<double>((size_t) p.n * p.in_len, false);
+	// R consecutive outputs span at most (R-1) d/n + 1 input rows more than one output does
+	op->g_pad = (int) (((long) (RS_R - 1) * p.d) / p.n + 2);
+	op->g_stride = p.in_len + 2 * op->g_pad;
+	op->d_G = dev_alloc<double>((size_t) p.n * op->g_stride, true);
 	if (!d_sinc || !d_S || !op->d_G) return nullptr;
 	CUDA_TRY(cudaMemcpyAsync(d_sinc, sinc.data(), sinc.size() * sizeof(double), cudaMemcpyHostToDevice, st), return nullptr);
 	LAUNCH(k_rs_sinc_dft, ceil_div(p.sinc_len + 1, 128), 128, 0, st, d_sinc, p.m_os, p.sinc_len, d_S);
-	LAUNCH(k_rs_table, ceil_div((long) p.n * p.in_len, 128), 128, 0, st, d_S, p.sinc_len, p.n, p.in_len, op->d_G);
+	LAUNCH(k_rs_table, ceil_div((long) p.n * p.in_len, 128), 128, 0, st, d_S, p.sinc_len, p.n, p.in_len, op->d_G, op->g_stride, op->g_pad);
 	CUDA_TRY(cudaStreamSynchronize(st), return nullptr);
 	dev_free(d_sinc);
 	dev_free(d_S);

@@ -24,6 +24,7 @@ SIGNATURES = {
     "dspb200_last_error": (C.c_char_p, []),
     "dspb200_device_count": (C.c_int, []),
     "dspb200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "dspb200_host_alloc_wc": (C.c_void_p, [C.c_size_t]),
     "dspb200_host_free": (None, [C.c_void_p]),
     "dspb200_kernel_launches": (C.c_longlong, []),
     "dspb200_profile_enable": (None, [C.c_int]),
@@ -109,10 +110,11 @@ def _as_dp(a):
 class PinnedArray:
     """float64 numpy view over page-locked host memory from dspb200_host_alloc()."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, write_combined=False):
         self.shape = tuple(int(s) for s in shape)
         n = int(np.prod(self.shape)) if self.shape else 1
-        self.ptr = lib().dspb200_host_alloc(max(n, 1) * 8)
+        alloc = lib().dspb200_host_alloc_wc if write_combined else lib().dspb200_host_alloc
+        self.ptr = alloc(max(n, 1) * 8)
         if not self.ptr:
             raise DspB200Error("host_alloc failed: " + last_error())
         buf = (C.c_double * max(n, 1)).from_address(self.ptr)

@@ -44,6 +44,7 @@ const char *dspb200_last_error(void);
 int  dspb200_device_count(void);                 /* CUDA devices visible; <= 0: none */
 /* Pinned host memory for callers that want the fast host path (bench e2e, frontends). */
 void *dspb200_host_alloc(size_t bytes);
+void *dspb200_host_alloc_wc(size_t bytes);       /* write-combined variant for input-only buffers */
 void  dspb200_host_free(void *p);
 /* Number of kernels this library has launched so far in this process (all chains). */
 long long dspb200_kernel_launches(void);
