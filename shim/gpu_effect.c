@@ -58,6 +58,7 @@ void gpu_part_free(struct gpu_part *p)
 		struct gpu_part *next = p->next;
 		free(p->selector);
 		free(p->bq);
+		free(p->gain);
 		free(p->taps);
 		free(p);
 		p = next;
@@ -85,11 +86,14 @@ static void gpu_effect_reset(struct effect *e)
 /* one part's transfer function on channel k, as a gnuplot expression in w */
 static void part_plot_expr(const struct gpu_part *p, int k)
 {
-	if (!GET_BIT(p->selector, k)) {
-		fputs("1.0", stdout);
+	if (!GET_BIT(p->selector, k) || (p->kind == GPU_PART_GAIN && p->is_add)) {
+		fputs("1.0", stdout);   /* `add` plots as unity, effect.c:96-100 */
 		return;
 	}
-	if (p->kind == GPU_PART_BIQUAD) {
+	if (p->kind == GPU_PART_GAIN) {
+		printf("%.15e", p->gain[k]);
+	}
+	else if (p->kind == GPU_PART_BIQUAD) {
 		printf("(" BIQUAD_PLOT_FMT ")", BIQUAD_PLOT_FMT_ARGS(&p->bq[k]));
 	}
 	else {
@@ -171,6 +175,7 @@ static int gpu_effect_merge(struct effect *dest, struct effect *src)
 	if (getenv("DSP_B200_NO_MERGE")) return 0;
 	/* the optimizer also offers pairs with skipped effects in between; only hop over effects that
 	 * declare themselves reorderable (LTI and channel-wise), so the signal path is unchanged */
+	if (dest->next != src && !(src->flags & EFFECT_FLAG_OPT_REORDERABLE)) return 0;
 	for (struct effect *between = dest->next; between && between != src; between = between->next)
 		if (!(between->flags & EFFECT_FLAG_OPT_REORDERABLE)) return 0;
 	if (dspb200_chain_absorb(d->chain, s->chain) != 0) return 0;
@@ -178,6 +183,7 @@ static int gpu_effect_merge(struct effect *dest, struct effect *src)
 	while (*tail) tail = &(*tail)->next;
 	*tail = s->parts;
 	s->parts = NULL;
+	if (!(src->flags & EFFECT_FLAG_OPT_REORDERABLE)) dest->flags &= ~EFFECT_FLAG_OPT_REORDERABLE;
 	if (!dest->drain_samples) dest->drain_samples = src->drain_samples;
 	if (!dest->channel_offsets) dest->channel_offsets = src->channel_offsets;
 	return 1;

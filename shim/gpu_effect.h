@@ -15,7 +15,7 @@
 #include "biquad.h"
 #include "dsp_b200.h"
 
-enum gpu_part_kind { GPU_PART_BIQUAD = 1, GPU_PART_FIR, GPU_PART_RESAMPLE };
+enum gpu_part_kind { GPU_PART_BIQUAD = 1, GPU_PART_FIR, GPU_PART_RESAMPLE, GPU_PART_GAIN };
 
 struct gpu_part {
 	struct gpu_part *next;
@@ -23,6 +23,9 @@ struct gpu_part {
 	char *selector;                 /* [channels], owned */
 	/* GPU_PART_BIQUAD */
 	struct biquad_state *bq;        /* [channels] coefficients (selected channels only), owned */
+	/* GPU_PART_GAIN */
+	sample_t *gain;                 /* [channels] multiplier (or addend when is_add), owned */
+	int is_add;
 	/* GPU_PART_FIR */
 	sample_t *taps;                 /* [frames][fc], owned (kept for plot) */
 	int fc;

@@ -57,9 +57,24 @@ def test_dropin_merge_fuses_gpu_effects(dropin):
                         "0.0000000002,0.0000000001,0.00000000005,0.00000000002,0.00000000001 eq 5k 2.0 1", 48000, 2, lib_path=DROPIN)
     assert len(c.effect_names()) == 1, c.effect_names()
     c.close()
-    # a CPU-only effect in between that is not reorderable keeps the order: two GPU groups
-    c = dropin.RefChain("eq 100 1.0 2 eq 1k 1.0 -2 add 0.001 eq 5k 2.0 1", 48000, 2, lib_path=DROPIN)
-    assert c.effect_names() == ["eq", "add", "eq"], c.effect_names()
+    # `add` is not reorderable but adjacent merging keeps the signal order: still one device chain, same result
+    spec = "eq 100 1.0 2 eq 1k 1.0 -2 add 0.001 eq 5k 2.0 1"
+    c = dropin.RefChain(spec, 48000, 2, lib_path=DROPIN)
+    assert len(c.effect_names()) == 1, c.effect_names()
+    x = np.random.default_rng(0).standard_normal((3000, 2)) * 0.1
+    y, _ = c.process(x, 700)
+    c.close()
+    if dropin.available():
+        r = dropin.RefChain(spec, 48000, 2)
+        want, _ = r.process(x, 700)
+        assert rms(y - want) <= RMS_TOL
+    # a reference CPU effect that is not reorderable splits the run: two GPU groups around it
+    c = dropin.RefChain("eq 100 1.0 2 eq 1k 1.0 -2 noise -100 eq 5k 2.0 1", 48000, 2, lib_path=DROPIN)
+    assert c.effect_names() == ["eq", "noise", "eq"], c.effect_names()
+    c.close()
+    # a reorderable CPU effect (delay.c) is hopped over, as the reference's own optimizer does for its effects
+    c = dropin.RefChain("eq 100 1.0 2 delay 5S eq 5k 2.0 1", 48000, 2, lib_path=DROPIN)
+    assert c.effect_names()[:2] == ["eq", "delay"] and "eq" not in c.effect_names()[1:], c.effect_names()
     c.close()
 
 
@@ -72,7 +87,7 @@ def test_dropin_matches_reference_on_c2(dropin, have_ref):
     x = dropin.sgen("sine:freq=20-20k+20000S", 48000, 16, 20000)
     a = dropin.RefChain(chain, 48000, 16)
     b = dropin.RefChain(chain, 48000, 16, lib_path=DROPIN)
-    assert b.effect_names() == ["gain", "eq"]          # reference gain (CPU) + ten biquads fused on the GPU
+    assert b.effect_names() == ["gain"]                # gain + ten biquads: ONE device chain (one H2D/D2H per block)
     ya, ca = a.process(x, 4096)
     yb, cb = b.process(x, 4096)
     assert ca == cb

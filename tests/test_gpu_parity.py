@@ -188,3 +188,27 @@ def test_device_resident_mode(gpu_lib):
     assert np.array_equal(ya, np.concatenate(outs))
     a.close()
     b.close()
+
+
+def test_in_process_multi_gpu_sharding(gpu_lib):
+    """One chain sharded over two GPUs in one process (DSP_B200_DEVICES in the shim): one strided host
+    scatter and gather per shard, no collective; bit-identical to the single-GPU chain."""
+    if gpu_lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    from oracle import restate
+    fs, C, F = 48000, 12, 1024
+    h = np.stack([restate.bench_ir(3000, c) for c in range(C)], axis=1)
+    coefs = eq_coefs(gpu_lib, fs, 3)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((5 * F, C)) * 0.2
+
+    def build(devices, slabs):
+        return gpu_lib.Chain(fs, C, devices=devices, slabs_per_device=slabs).add_biquad(coefs).add_fir(h, block_hint=F).add_resample(44100)
+    a, b = build([0], 1), build([0, 1], 2)
+    assert b.n_shards == 4 and {b.shard_info(i)[0] for i in range(4)} == {0, 1}
+    ya, ca = a.process(x, F)
+    yb, cb = b.process(x, F)
+    assert ca == cb
+    assert np.array_equal(ya, yb)
+    a.close()
+    b.close()
