@@ -203,8 +203,9 @@ struct Shard {
 	}
 
 	// run ops[first..) over `frames` frames: in -> out (device pointers, this shard's slab)
-	long run_ops(size_t first, long frames, const double *in, double *out, bool in_writable, cudaStream_t st)
+	long run_ops(size_t first, long frames, const double *in, double *out, bool in_writable, cudaStream_t st, bool host_mode = true)
 	{
+		for (auto &op : ops) op->host_mode = host_mode;
 		const double *cur = in;
 		bool cur_writable = in_writable || (in == out);
 		long f = frames;
@@ -594,7 +595,7 @@ long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const do
 	CUDA_TRY(cudaSetDevice(s->device), return -1);
 	if (s->ensure_cap(frames)) return -1;
 	cudaStream_t st = (cudaStream_t) stream;   // NULL = the legacy default stream, as everywhere in CUDA
-	return s->run_ops(0, frames, d_in, d_out, false, st);
+	return s->run_ops(0, frames, d_in, d_out, false, st, false);
 }
 
 long dspb200_chain_drain_host(dspb200_chain *c, long frames, double *out)

@@ -248,6 +248,18 @@ struct L0Args {
 	int n_ch;
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// pull `bytes` starting at p towards L2, one request per 128-byte line, spread over the FFT's T threads
+__device__ __forceinline__ void prefetch_rows(const void *p, long bytes, int t, int T)
+{
+	const char *c = static_cast<const char *>(p);
+	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) prefetch_l2(c + off);
+}
+
 __device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 h)
 {
 	return make_double2(fma(x.x, h.x, fma(-x.y, h.y, acc.x)), fma(x.x, h.y, fma(x.y, h.x, acc.y)));
@@ -268,6 +280,19 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 		double2 v[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) v[i] = x[t + i * T];
+		// what the middle and the last phase will read from HBM: start it moving towards L2 now, so that it
+		// arrives while the first transform runs (the CTA's warps all sit in the same phase, nothing else hides it)
+		{
+			const double2 *Hc = a.H + (long) s * a.h_ch_stride;
+			prefetch_rows(Hc, (long) P * N * sizeof(double2), t, T);
+			const double2 *fc_ = a.fdl + (long) s * a.fdl_ch_stride;
+#pragma unroll
+			for (int p = 1; p < P; ++p) {
+				const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
+				prefetch_rows(fc_ + (long) sl * N, (long) N * sizeof(double2), t, T);
+			}
+			prefetch_rows(a.carry + (long) s * N, (long) N * sizeof(double), t, T);
+		}
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			buf[spad(t + i * T)] = v[i];
@@ -812,29 +837,39 @@ struct FirOp : Op {
 	//     period q+2, so the HBM-streaming MAC has a whole period to overlap with the FFT kernels.
 	int advance_upper_levels(cudaStream_t st)
 	{
+		// Everything goes to the side stream: in host mode the D2H of this block and the H2D of the next are not
+		// held up, and in device-resident mode it measured faster too (7.1 vs 6.6 Gsamples/s with the
+		// partition-0 kernels on the caller's stream): the caller's stream keeps only stash, level 0, unstash.
+		cudaStream_t us = side;
 		bool any = false;
 		for (int l = 1; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			if (abs_pos % L.B != 0) break;   // sizes double: if this one is not complete, none above is
-			if (!any) {
+			if (!any && us == side) {
 				CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
 				CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
-				any = true;
 			}
+			any = true;
 			L0Args f = {};
 			f.in = d_hist + (L.blk * L.B) % hist_len; f.in_ch_stride = hist_len;
 			f.fdl = L.fdl; f.fdl_ch_stride = (long) L.P * L.B; f.fdl_rows = L.P;
 			f.H = L.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 			f.P = 1; f.slot = (int) (L.blk % L.P);
 			f.out = L.pend; f.out_ch_stride = L.B; f.carry = L.carry; f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
-			if (launch_level0(L.B, f, side)) return -1;
+			if (launch_level0(L.B, f, us)) return -1;
 			++L.blk;
 		}
 		if (!any) return 0;
-		CUDA_TRY(cudaEventRecord(ev_urgent, side), return -1);
-		urgent_pending = true;
+		if (us == side) {
+			CUDA_TRY(cudaEventRecord(ev_urgent, side), return -1);
+			urgent_pending = true;
+		}
 		FirLevel &L = lv[n_levels - 1];
 		if (L.carry_tail && abs_pos % L.B == 0) {
+			if (us != side) {
+				CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
+				CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
+			}
 			const long q1 = L.blk;   // R_{q+1}, q = the block that just completed
 			mac(L, 1, L.P, q1, side, d_Y_side);
 			InvArgs v = {};
