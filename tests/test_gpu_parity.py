@@ -212,3 +212,22 @@ def test_in_process_multi_gpu_sharding(gpu_lib):
     assert np.array_equal(ya, yb)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("block,taps", [(8192, 70000), (10000, 20000), (65536, 20000), (300, 40000)])
+def test_fir_p_large_and_odd_blocks(gpu_lib, block, taps):
+    """Partition = 8192 with many partitions (single level, three-kernel path), calls longer than the largest
+    partition, and a small odd block with a long filter (four levels)."""
+    from oracle import restate
+    fs, C = 48000, 4
+    rng = np.random.default_rng(block + taps)
+    h = restate.bench_ir(taps)
+    N = max(3 * block, 2 * taps) + 77
+    x = rng.standard_normal((N, C)) * 0.2
+    want = restate.fir_stream(x, h)
+    ch = gpu_lib.Chain(fs, C).add_fir(h)
+    got = np.concatenate([ch.run(x[i:i + block]).copy() for i in range(0, N, block)])
+    plan = ch.describe()[0]
+    assert plan["planned"] == 1
+    assert rms(got - want) <= RMS_TOL, (plan, rms(got - want))
+    ch.close()
