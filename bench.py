@@ -272,7 +272,17 @@ def main():
     # with several levels, partition 0 of the last level is done inline by the fused kernel; the MAC streams the other P-1
     mac_parts = lvl["P"] - 1 if len(plan["levels"]) > 1 else lvl["P"]
     mac_bytes = C * lvl["B"] * 16.0 * (mac_parts * (1 + h) + 1)
+    tb = int(plan.get("t_batch", 0))
+    if tb:
+        # time-batched tail: every period k_fir_mac streams partitions 1..T plus the batched spectrum (read) and writes Y;
+        # every T periods k_fir_mac_batch streams the other FDL rows and filter rows once for T outputs
+        mac_parts = tb
+        mac_bytes = C * lvl["B"] * 16.0 * (tb * (1 + h) + 2)
+    batch_bytes = C * lvl["B"] * 16.0 * ((lvl["P"] - 2) + (lvl["P"] - tb - 1) * h + tb) if tb else 0.0
     step_bytes = sum(C * L["B"] * 16.0 * (L["P"] * (1 + h) + 1) * (F / L["B"]) for L in plan["levels"])
+    if tb:
+        step_bytes = (C * plan["levels"][0]["B"] * 16.0 * (plan["levels"][0]["P"] * (1 + h) + 1)
+                      + (C * lvl["B"] * 16.0 * (1 + h + 1) + mac_bytes + batch_bytes / tb) * (F / lvl["B"]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -288,6 +298,7 @@ def main():
         pass
     roofline = None
     head_ms, head_n = dsp_b200.profile_read("fir_mac_head")
+    batch_ms, batch_n = dsp_b200.profile_read("fir_mac_batch")
     if mac_n > 0:
         mac_avg_s = mac_ms / mac_n * 1e-3
         ach = mac_bytes / mac_avg_s / 1e9
@@ -296,9 +307,48 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": mac_bytes, "avg_launch_us": mac_avg_s * 1e6, "launches": mac_n,
                     "share_of_step": mac_ms / ms if ms > 0 else None,
-                    "partition_levels": plan["levels"], "mac_bytes_per_step_all_levels": step_bytes,
+                    "partition_levels": plan["levels"], "t_batch": tb, "mac_bytes_per_step_all_levels": step_bytes,
+                    "batch_kernel": ({"kernel": "k_fir_mac_batch", "algorithmic_bytes_per_launch": batch_bytes, "avg_launch_us": batch_ms / batch_n * 1e3,
+                                      "achieved_GBs": batch_bytes / (batch_ms / batch_n * 1e-3) / 1e9, "launches": batch_n} if batch_n else None),
                     "other_kernels_us_per_step": {"k_fir_fwd": fwd_ms / steps * 1e3, "k_fir_inv": inv_ms / steps * 1e3,
                                                   "k_fir_mac_head": head_ms / steps * 1e3, "k_fir_level0": dsp_b200.profile_read("fir_level0")[0] / steps * 1e3, "k_fir_mac": mac_ms / steps * 1e3}}
+    # isolated kernel durations: a short extra pass with the side streams folded into the caller's stream
+    iso = {}
+    dsp_b200.debug_serialize(True)
+    for i in range(2 * 8):
+        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    names = ("fir_mac", "fir_mac_batch", "fir_level0", "fir_inv")
+    for nme in names:
+        dsp_b200.profile_read(nme)
+    dsp_b200.profile_enable(True)
+    for i in range(8 * 8):
+        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    dsp_b200.profile_enable(False)
+    dsp_b200.debug_serialize(False)
+    for nme in names:
+        t_ms, n_l = dsp_b200.profile_read(nme)
+        if n_l:
+            iso[nme] = t_ms / n_l * 1e3
+    if roofline is not None:
+        if "fir_mac" in iso:
+            roofline["isolated"] = {"avg_launch_us": iso["fir_mac"], "achieved": mac_bytes / (iso["fir_mac"] * 1e-6) / 1e9,
+                                    "frac": mac_bytes / (iso["fir_mac"] * 1e-6) / 1e9 / peak,
+                                    "note": "same kernel with the side streams folded into one stream (no concurrent kernels competing for HBM)"}
+        if tb and "fir_mac_batch" in iso and roofline.get("batch_kernel"):
+            roofline["batch_kernel"]["isolated_us"] = iso["fir_mac_batch"]
+            roofline["batch_kernel"]["isolated_GBs"] = batch_bytes / (iso["fir_mac_batch"] * 1e-6) / 1e9
+            roofline["batch_kernel"]["isolated_frac"] = roofline["batch_kernel"]["isolated_GBs"] / peak
+        roofline["isolated_kernel_us"] = iso
+        # all kernels of a step against the byte budget of the plan
+        B0 = plan["levels"][0]["B"]
+        per_sample = 16 + 32 + (8 + 16 * (2 * plan["levels"][0]["P"] - 1) * (1 if h else 0.5) + 16 + 8 + 8 + 8)
+        if len(plan["levels"]) > 1:
+            per_sample += (8 + 16 * h + 8 + 16 + 8 + 8) + mac_bytes / (C * lvl["B"]) + 40 + (batch_bytes / tb if tb else 0.0) / (C * lvl["B"])
+        roofline["step"] = {"algorithmic_bytes_per_sample": per_sample, "achieved": per_sample * C * F / (ms / steps * 1e-3) / 1e9,
+                            "frac": per_sample * C * F / (ms / steps * 1e-3) / 1e9 / peak,
+                            "note": "every kernel of the step (stash, fused level 0, unstash, level-1 partition 0, MACs, inverse) over the step time"}
     chain.close()
     del chain
 

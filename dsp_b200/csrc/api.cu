@@ -318,6 +318,8 @@ long long dspb200_kernel_launches(void) { return g_kernel_launches.load(); }
 
 void dspb200_profile_enable(int on) { g_profile_on.store(on ? 1 : 0); }
 
+void dspb200_debug_serialize(int on) { fir_debug_serialize(on); }
+
 int dspb200_profile_read(const char *name, double *total_ms, long *launches)
 {
 	std::lock_guard<std::mutex> lk(g_prof_lock);

@@ -36,6 +36,8 @@
 
 namespace dspb200 {
 
+std::atomic<int> g_fir_serialize{0};   // dspb200_debug_serialize(): no side streams (isolated kernel timings)
+
 constexpr int FIR_MAX_LEVELS = 8;
 constexpr int FIR_MAX_B = 8192;
 
@@ -391,6 +393,7 @@ struct MacArgs {
 	const double2 *fdl;   // [s][P][N]
 	const double2 *H;     // [s][P][N] or [P][N]
 	double2 *Y;           // [s][N]
+	const double2 *init;  // [s][N] spectrum to start from (NULL: zero)
 	int N, P;
 	int slot0, p0, p1;
 	long h_ch_stride;     // P*N or 0 (shared IR)
@@ -403,7 +406,8 @@ __global__ void __launch_bounds__(256) k_fir_mac(MacArgs a)
 	const int s = blockIdx.y;
 	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
-	double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+	double2 acc0 = a.init ? __ldcs(&a.init[(long) s * a.N + k]) : make_double2(0.0, 0.0);
+	double2 acc1 = make_double2(0.0, 0.0), acc2 = acc1, acc3 = acc1;
 	const bool dc = (k == 0);
 	int slot = a.slot0 - a.p0;
 	slot %= a.P;
@@ -446,6 +450,67 @@ __global__ void __launch_bounds__(256) k_fir_mac(MacArgs a)
 #undef CMAC
 	a.Y[(long) s * a.N + k] = make_double2((acc0.x + acc1.x) + (acc2.x + acc3.x), (acc0.y + acc1.y) + (acc2.y + acc3.y));
 }
+
+// Time-batched tail of the last level.  With V_j = sum_{p > T} X_{j-p} H_p (the part of block period j's
+// spectrum that only involves blocks at least T+1 periods old), one launch after block q completes produces
+// V_j for the T periods j = q+2 .. q+T+1 at once: every FDL row and every filter row is streamed ONCE for T
+// outputs (the filter rows slide through a T-deep register window), instead of once per output.
+// Y_t[k] = sum_{m=2}^{P-1} X_{q+2-m}[k] * H_{m+t}[k] over the (m, t) with T < m+t < P.
+struct MacBatchArgs {
+	const double2 *fdl;   // [s][P][N]
+	const double2 *H;     // [s][P][N] or [P][N]
+	double2 *V;           // [slot][s][N], slot = j mod n_slots
+	int N, P, n_sel;
+	long q;               // block that just completed
+	int n_slots;
+	long h_ch_stride;
+};
+
+template <int T, bool SHARED_H>
+__global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int s = blockIdx.y;
+	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
+	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
+	const bool dc = (k == 0);
+	const double2 zero = make_double2(0.0, 0.0);
+	double2 acc[T], hw[T];
+#define HROW(p) (((p) > T && (p) < a.P) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		acc[t] = zero;
+		hw[t] = HROW(2 + t);
+	}
+	int slot = (int) ((a.q + 2 - 2) % a.P);   // row of X_{q+2-m} for m = 2
+	for (int m = 2; m < a.P; ++m) {
+		const double2 x = __ldcs(&fdl[(long) slot * a.N]);
+		const double2 hnext = HROW(m + T);
+#pragma unroll
+		for (int t = 0; t < T; ++t) {
+			if (dc) {
+				acc[t].x = fma(x.x, hw[t].x, acc[t].x);
+				acc[t].y = fma(x.y, hw[t].y, acc[t].y);
+			}
+			else {
+				acc[t].x = fma(x.x, hw[t].x, fma(-x.y, hw[t].y, acc[t].x));
+				acc[t].y = fma(x.x, hw[t].y, fma(x.y, hw[t].x, acc[t].y));
+			}
+		}
+#pragma unroll
+		for (int t = 0; t + 1 < T; ++t) hw[t] = hw[t + 1];
+		hw[T - 1] = hnext;
+		slot = (slot == 0) ? a.P - 1 : slot - 1;
+	}
+#undef HROW
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		const long j = a.q + 2 + t;
+		a.V[((j % a.n_slots) * a.n_sel + s) * (long) a.N + k] = acc[t];
+	}
+}
+
+constexpr int FIR_T_BATCH = 4;
 
 // general path: out[m] = pre[m] + pend(m) + sum_{r<=m} x[r] h0[m-r], m = pos+i; x = current level-0 block in the ring
 __global__ void k_fir_head(const double *hist, long hist_len, long blk_off, const double *pre, const double *h0, long h0_ch_stride,
@@ -571,6 +636,8 @@ static void launch_mac(const MacArgs &a, int n_sel, bool shared_h, const char *p
 // ------------------------------------------------------------------------------------------
 // unit-test hooks (tests/ only): packed real FFT round trip
 // ------------------------------------------------------------------------------------------
+void fir_debug_serialize(int on) { g_fir_serialize.store(on ? 1 : 0); }
+
 int test_rfft(int B, int n_ch, const double *d_in, double *d_spec, cudaStream_t st)
 {
 	FwdArgs a = {};
@@ -650,6 +717,11 @@ struct FirOp : Op {
 	// side stream: the last level's tail (MAC over p >= 1 + inverse) overlaps the main stream's next period
 	cudaStream_t side = nullptr;
 	cudaEvent_t ev_main = nullptr, ev_urgent = nullptr, ev_side[2] = { nullptr, nullptr };
+	// time-batched tail (see k_fir_mac_batch): V spectra for 2 T block periods, produced T at a time on a second side stream
+	int t_batch = 0;
+	double2 *d_V = nullptr;
+	cudaStream_t side2 = nullptr;
+	cudaEvent_t ev_batch[2] = { nullptr, nullptr }, ev_main2 = nullptr;
 	long waited_period = -1;
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
@@ -665,7 +737,7 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "]}");
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d}", t_batch);
 		return buf;
 	}
 
@@ -675,6 +747,14 @@ struct FirOp : Op {
 			cudaStreamSynchronize(side);
 			cudaStreamDestroy(side);
 		}
+		if (side2) {
+			cudaStreamSynchronize(side2);
+			cudaStreamDestroy(side2);
+		}
+		for (cudaEvent_t e : ev_batch)
+			if (e) cudaEventDestroy(e);
+		if (ev_main2) cudaEventDestroy(ev_main2);
+		dev_free(d_V);
 		if (ev_main) cudaEventDestroy(ev_main);
 		if (ev_urgent) cudaEventDestroy(ev_urgent);
 		for (cudaEvent_t e : ev_side)
@@ -737,6 +817,18 @@ struct FirOp : Op {
 				L.pend_tail[1] = dev_alloc<double>((size_t) n_sel * L.B);
 				d_Y_side = dev_alloc<double2>((size_t) n_sel * L.B);
 				if (!L.carry_tail || !L.pend_tail[0] || !L.pend_tail[1] || !d_Y_side) return -1;
+				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
+				if (L.P >= 2 * FIR_T_BATCH + 2 && !(nb && nb[0] == '1')) {
+					t_batch = FIR_T_BATCH;
+					d_V = dev_alloc<double2>((size_t) 2 * t_batch * n_sel * L.B);
+					if (!d_V) return -1;
+					int lo = 0, hi = 0;
+					cudaDeviceGetStreamPriorityRange(&lo, &hi);
+					CUDA_TRY(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, lo), return -1);
+					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[0], cudaEventDisableTiming), return -1);
+					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[1], cudaEventDisableTiming), return -1);
+					CUDA_TRY(cudaEventCreateWithFlags(&ev_main2, cudaEventDisableTiming), return -1);
+				}
 			}
 			if (L.B > Bmax) Bmax = L.B;
 		}
@@ -785,6 +877,8 @@ struct FirOp : Op {
 		abs_pos = 0; pre_valid = false; waited_period = -1; urgent_pending = false;
 		if (!planned) return;
 		if (side) cudaStreamSynchronize(side);
+		if (side2) cudaStreamSynchronize(side2);
+		if (d_V) cudaMemsetAsync(d_V, 0, (size_t) 2 * t_batch * n_sel * lv[n_levels - 1].B * sizeof(double2), st);
 		for (int l = 0; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			L.blk = 0;
@@ -801,10 +895,10 @@ struct FirOp : Op {
 		if (d_ring) cudaMemsetAsync(d_ring, 0, (size_t) latency * n_sel * sizeof(double), st);
 	}
 
-	void mac(FirLevel &L, int p0, int p1, long slot_blk, cudaStream_t st, double2 *Y = nullptr)
+	void mac(FirLevel &L, int p0, int p1, long slot_blk, cudaStream_t st, double2 *Y = nullptr, const double2 *init = nullptr)
 	{
 		MacArgs m = {};
-		m.fdl = L.fdl; m.H = L.H; m.Y = Y ? Y : d_Y; m.N = L.B; m.P = L.P;
+		m.fdl = L.fdl; m.H = L.H; m.Y = Y ? Y : d_Y; m.init = init; m.N = L.B; m.P = L.P;
 		m.slot0 = (int) (slot_blk % L.P); m.p0 = p0; m.p1 = p1;
 		m.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 		// the last level carries (almost) all the taps: it is the kernel the roofline line is about
@@ -840,12 +934,13 @@ struct FirOp : Op {
 		// Everything goes to the side stream: in host mode the D2H of this block and the H2D of the next are not
 		// held up, and in device-resident mode it measured faster too (7.1 vs 6.6 Gsamples/s with the
 		// partition-0 kernels on the caller's stream): the caller's stream keeps only stash, level 0, unstash.
-		cudaStream_t us = side;
+		const bool serial = g_fir_serialize.load(std::memory_order_relaxed) != 0;
+		cudaStream_t us = serial ? st : side, ts = us, bs = serial ? st : side2;
 		bool any = false;
 		for (int l = 1; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			if (abs_pos % L.B != 0) break;   // sizes double: if this one is not complete, none above is
-			if (!any && us == side) {
+			if (!any && us != st) {
 				CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
 				CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
 			}
@@ -860,23 +955,44 @@ struct FirOp : Op {
 			++L.blk;
 		}
 		if (!any) return 0;
-		if (us == side) {
-			CUDA_TRY(cudaEventRecord(ev_urgent, side), return -1);
-			urgent_pending = true;
-		}
+		CUDA_TRY(cudaEventRecord(ev_urgent, us), return -1);
+		urgent_pending = (us != st);
 		FirLevel &L = lv[n_levels - 1];
 		if (L.carry_tail && abs_pos % L.B == 0) {
-			if (us != side) {
-				CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
-				CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
-			}
 			const long q1 = L.blk;   // R_{q+1}, q = the block that just completed
-			mac(L, 1, L.P, q1, side, d_Y_side);
+			if (t_batch > 0) {
+				// R_j = U_j + V_j, j = q1: U_j = sum_{1<=p<=T} X_{j-p} H_p now, V_j from the batch launched at
+				// the end of period T*floor((j-2)/T) (zero before the first batch: those blocks do not exist)
+				const int T = t_batch;
+				if (q1 >= 2) {
+					const long qb = ((q1 - 2) / T) * T;
+					CUDA_TRY(cudaStreamWaitEvent(ts, ev_batch[(qb / T) & 1], 0), return -1);
+				}
+				const double2 *init = d_V + (size_t) (q1 % (2 * T)) * n_sel * L.B;
+				mac(L, 1, T + 1, q1, ts, d_Y_side, init);
+			}
+			else mac(L, 1, L.P, q1, ts, d_Y_side);
 			InvArgs v = {};
 			v.Y = d_Y_side; v.out = L.pend_tail[q1 & 1]; v.out_ch_stride = L.B; v.carry = L.carry_tail;
 			v.flags = INV_OUT | INV_UPDATE_CARRY; v.tw = L.tw; v.ptw = L.ptw; v.n_ch = n_sel;
-			if (launch_inv(L.B, v, side)) return -1;
-			CUDA_TRY(cudaEventRecord(ev_side[q1 & 1], side), return -1);
+			if (launch_inv(L.B, v, ts)) return -1;
+			CUDA_TRY(cudaEventRecord(ev_side[q1 & 1], ts), return -1);
+			const long q = q1 - 1;
+			if (t_batch > 0 && q % t_batch == 0) {
+				// X_q is in the FDL once the partition-0 kernel of this block has run (ev_urgent on the side stream)
+				CUDA_TRY(cudaStreamWaitEvent(bs, ev_urgent, 0), return -1);
+				MacBatchArgs b = {};
+				b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
+				b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+				const int threads = (L.B < 256) ? L.B : 256;
+				dim3 grid(L.B / threads, n_sel);
+				{
+					ProfScope prof("fir_mac_batch", bs);
+					if (fc == 1) LAUNCH((k_fir_mac_batch<FIR_T_BATCH, true>), grid, threads, 0, bs, b);
+					else LAUNCH((k_fir_mac_batch<FIR_T_BATCH, false>), grid, threads, 0, bs, b);
+				}
+				CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
+			}
 		}
 		return 0;
 	}

@@ -28,6 +28,7 @@ SIGNATURES = {
     "dspb200_host_free": (None, [C.c_void_p]),
     "dspb200_kernel_launches": (C.c_longlong, []),
     "dspb200_profile_enable": (None, [C.c_int]),
+    "dspb200_debug_serialize": (None, [C.c_int]),
     "dspb200_profile_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), _lp]),
     "dspb200_chain_create": (C.c_void_p, [C.c_int, C.c_int, _ip, C.c_int, C.c_int]),
     "dspb200_chain_destroy": (None, [C.c_void_p]),
@@ -88,6 +89,10 @@ def kernel_launches():
 
 def profile_enable(on):
     lib().dspb200_profile_enable(1 if on else 0)
+
+
+def debug_serialize(on):
+    lib().dspb200_debug_serialize(1 if on else 0)
 
 
 def profile_read(name):

@@ -55,6 +55,9 @@ long long dspb200_kernel_launches(void);
  * the summed milliseconds and the launch count since the last read, and clears them. */
 void dspb200_profile_enable(int on);
 int  dspb200_profile_read(const char *name, double *total_ms, long *launches);
+/* Measurement aid: while on, operators that normally overlap work on side streams enqueue everything on the
+ * caller's stream, so per-kernel durations are free of contention (results are identical either way). */
+void dspb200_debug_serialize(int on);
 
 /* ---- chain construction ---------------------------------------------------------------- */
 /* devices[n_devices]: CUDA ordinals to shard over (NULL/0: device 0).  slabs_per_device >= 1
