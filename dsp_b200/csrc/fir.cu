@@ -483,25 +483,42 @@ __global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
 		hw[t] = HROW(2 + t);
 	}
 	int slot = (int) ((a.q + 2 - 2) % a.P);   // row of X_{q+2-m} for m = 2
-	for (int m = 2; m < a.P; ++m) {
-		const double2 x = __ldcs(&fdl[(long) slot * a.N]);
-		const double2 hnext = HROW(m + T);
-#pragma unroll
-		for (int t = 0; t < T; ++t) {
-			if (dc) {
-				acc[t].x = fma(x.x, hw[t].x, acc[t].x);
-				acc[t].y = fma(x.y, hw[t].y, acc[t].y);
-			}
-			else {
-				acc[t].x = fma(x.x, hw[t].x, fma(-x.y, hw[t].y, acc[t].x));
-				acc[t].y = fma(x.x, hw[t].y, fma(x.y, hw[t].x, acc[t].y));
-			}
-		}
-#pragma unroll
-		for (int t = 0; t + 1 < T; ++t) hw[t] = hw[t + 1];
-		hw[T - 1] = hnext;
+#define XROW(d) __ldcs(&fdl[(long) ((slot - (d) < 0) ? slot - (d) + a.P : slot - (d)) * a.N])
+#define STEP(XV, HN)                                                          \
+	do {                                                                      \
+		_Pragma("unroll") for (int t = 0; t < T; ++t) {                       \
+			if (dc) {                                                         \
+				acc[t].x = fma(XV.x, hw[t].x, acc[t].x);                      \
+				acc[t].y = fma(XV.y, hw[t].y, acc[t].y);                      \
+			}                                                                 \
+			else {                                                            \
+				acc[t].x = fma(XV.x, hw[t].x, fma(-XV.y, hw[t].y, acc[t].x)); \
+				acc[t].y = fma(XV.x, hw[t].y, fma(XV.y, hw[t].x, acc[t].y));  \
+			}                                                                 \
+		}                                                                     \
+		_Pragma("unroll") for (int t = 0; t + 1 < T; ++t) hw[t] = hw[t + 1];  \
+		hw[T - 1] = HN;                                                       \
+	} while (0)
+	int m = 2;
+	for (; m + 4 <= a.P; m += 4) {
+		// eight independent 16-byte loads in flight per thread, as in k_fir_mac
+		const double2 x0 = XROW(0), x1 = XROW(1), x2 = XROW(2), x3 = XROW(3);
+		const double2 h0 = HROW(m + T), h1 = HROW(m + T + 1), h2 = HROW(m + T + 2), h3 = HROW(m + T + 3);
+		STEP(x0, h0);
+		STEP(x1, h1);
+		STEP(x2, h2);
+		STEP(x3, h3);
+		slot -= 4;
+		if (slot < 0) slot += a.P;
+	}
+	for (; m < a.P; ++m) {
+		const double2 x0 = XROW(0);
+		const double2 h0 = HROW(m + T);
+		STEP(x0, h0);
 		slot = (slot == 0) ? a.P - 1 : slot - 1;
 	}
+#undef XROW
+#undef STEP
 #undef HROW
 #pragma unroll
 	for (int t = 0; t < T; ++t) {
