@@ -41,6 +41,8 @@ std::mutex g_prof_lock;
 std::map<std::string, std::vector<ProfRec>> g_prof;
 }
 
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;   // recycled event pairs (creation is slow)
+
 void prof_mark(const char *name, cudaStream_t st, bool begin)
 {
 	std::lock_guard<std::mutex> lk(g_prof_lock);
@@ -49,7 +51,12 @@ void prof_mark(const char *name, cudaStream_t st, bool begin)
 		ProfRec r;
 		r.closed = false;
 		cudaGetDevice(&r.device);
-		if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+		if (!g_prof_pool.empty()) {
+			r.a = g_prof_pool.back().first;
+			r.b = g_prof_pool.back().second;
+			g_prof_pool.pop_back();
+		}
+		else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
 		cudaEventRecord(r.a, st);
 		v.push_back(r);
 	}
@@ -333,8 +340,7 @@ int dspb200_profile_read(const char *name, double *total_ms, long *launches)
 				float t = 0.0f;
 				if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; ++n; }
 			}
-			cudaEventDestroy(r.a);
-			cudaEventDestroy(r.b);
+			g_prof_pool.push_back({ r.a, r.b });   // single-device use: events go back to the pool
 		}
 		it->second.clear();
 	}

@@ -1,279 +1,166 @@
-// biquad.cu -- K1: fused, time-parallel biquad cascade.
+// biquad.cu -- K1: fused, time-parallel biquad cascade (one kernel, one read + one write of the block).
 //
-// Reference behaviour reproduced (/root/reference): biquad() biquad.h:76-92 (transposed direct
-// form II), applied in place per channel by biquad_effect_run[_all] biquad.c:296-315, one pass
-// over the block PER STAGE.  Here a cascade of S stages is ONE operator and one read + one write
-// of the block.
+// Reference behaviour reproduced (/root/reference): biquad() biquad.h:76-92 (transposed direct form II),
+// applied in place per channel by biquad_effect_run[_all] biquad.c:296-315 -- one pass over the block PER
+// STAGE there; here a cascade of S stages is ONE operator.
 //
 // Per stage (biquad.h:79-81):   r = c0 s + m0;  m0' = m1 + c1 s - c3 r;  m1' = c2 s - c4 r
-// The cascade is a linear system with state z = (m0,m1 of every stage) in R^D, D = 2S.  Time is
-// cut into chunks of L frames; thread (channel c, chunk j):
-//   k_bq_local  runs the cascade over its chunk from ZERO state, keeps only the end state b_j
-//   k_bq_scan   one CTA per channel: z_{j+1} = M_c z_j + b_j, z_0 = carried state, M_c = A_c^L, evaluated
-//               hierarchically in groups of 8 chunks (A_c = zero-input transition of the cascade, powers
-//               M_c^1..M_c^8 taken on the host in long double)
-//   k_bq_apply  re-runs the cascade over the chunk from its TRUE start state z_j and stores
-// so every output sample is produced by the reference's own recurrence, started from a state
-// that differs from the sequential one only by rounding in the scan (|eig A| < 1).
-// Lanes run along channels: every global access is a coalesced row of the interleaved block.
+// i.e. the state z = (m0, m1) follows z' = A z + B s with A = [[-c3, 1], [-c4, 0]] (zero-input step).
+// The per-sample recurrence is parallelised along TIME as an associative scan over these affine maps:
+//   * a CTA owns one channel; its 128 threads own 128 consecutive chunks of L = 32 frames (lanes run
+//     along time), the chunk's samples live in registers through all S stages;
+//   * per stage: (1) every lane needs the end state e its chunk would reach from a ZERO state; that is the
+//     dot product e = sum_i A^(L-1-i) B s_i of the chunk with a per-stage table (64 independent FMAs instead of
+//     a serial recurrence; table built on the host in long double); (2) warp-level inclusive scan of the states by shuffles -- all chunks share the matrix
+//     A^L, so round r is  s += A^(L 2^r) shfl_up(s, 2^r)  with the five powers taken on the host in long
+//     double; (3) warp totals are chained through shared memory with A^(32 L), every lane turns the
+//     carry-in of its warp into its own start state with the binary expansion of its lane index;
+//     (4) the lane re-runs the reference's own recurrence from that TRUE start state -- so every output
+//     sample is produced by exactly the reference's arithmetic, started from a state that differs from the
+//     sequential one only by rounding in the scan (|eig A| < 1);
+//   * longer calls loop over tiles of 128 chunks, carrying the per-stage state through shared memory.
+// A stage that does not act on a channel carries the identity section {1,0,0,0,0}.
+// Global accesses are 8-byte loads/stores strided by the channel count (a lane's 32 frames); the four
+// channels sharing each 32-byte sector are read by neighbouring CTAs at about the same time, so HBM
+// sees every sector once (L2 absorbs the rest).  Algorithmic bytes: 16 per sample.
 #include "common.cuh"
 #include "ops.h"
 
 namespace dspb200 {
 
-constexpr int BQ_L = 32;          // frames per chunk
-constexpr int BQ_MAX_STAGES = 16; // D <= 32: one lane per state component in the scan
+constexpr int BQ_L = 16;           // frames per lane
+constexpr int BQ_WARPS = 8;        // warps per CTA: 256 chunks = 4096 frames per tile
+constexpr int BQ_MAX_STAGES = 16;  // stages fused into one operator
+constexpr int BQ_NPOW = 6;         // A^(L 2^r), r = 0..5 (r = 5: one warp's span)
+// per channel and stage: 5 coefficients, BQ_NPOW 2x2 matrices, and G[i] = A^(L-1-i) B (2 x L), contiguous
+constexpr int BQ_TBL = 5 + 4 * BQ_NPOW + 2 * BQ_L;
 
-// coef layout: [stage][5][C]; state layouts: b, zin: [c][chunk][D]; zstate: [c][D]
-//
-// Stages are processed in groups of G, software-pipelined across the samples of the chunk (stage g works
-// on sample t-g at step t): the G recurrences are independent dependency chains, so the FP64 pipe sees G-fold
-// instruction-level parallelism instead of one serial chain, and the G*5 coefficients of a group are fetched
-// together (one exposed load latency per group instead of one per stage).
-template <bool APPLY, int G>
-__device__ __forceinline__ void bq_stage_group(double (&y)[BQ_L], int nv, const double *__restrict__ coef, int C, int c, int st0, int ng,
-                                               const double *z0, double *zend, bool store_end)
+struct M2 { double a, b, c, d; };  // [[a, b], [c, d]]
+
+__device__ __forceinline__ double2 m2_apply(const M2 &m, double2 v)
 {
-	double c0[G], c1[G], c2[G], c3[G], c4[G], m0[G], m1[G];
+	return make_double2(fma(m.a, v.x, m.b * v.y), fma(m.c, v.x, m.d * v.y));
+}
+
+// tbl: [C][S][BQ_TBL] (see BQ_TBL), zstate: [C][S][2]
+__global__ void __launch_bounds__(32 * BQ_WARPS) k_bq_cascade(const double *in, double *out, const double *__restrict__ tbl,
+                                                             double *zstate, int C, int S, long frames)
+{
+	__shared__ double2 tot[BQ_WARPS];
+	__shared__ double2 carry[BQ_MAX_STAGES];
+	extern __shared__ double stbl[];   // [S][BQ_TBL]: this channel's tables (every lane reads the same entries: broadcasts)
+	const int c = blockIdx.x;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < S * BQ_TBL; i += blockDim.x) stbl[i] = tbl[(long) c * S * BQ_TBL + i];
+	if (threadIdx.x < S) carry[threadIdx.x] = make_double2(zstate[((long) c * S + threadIdx.x) * 2], zstate[((long) c * S + threadIdx.x) * 2 + 1]);
+	__syncthreads();
+
+	const long tile_frames = (long) BQ_L * 32 * BQ_WARPS;
+	for (long base = 0; base < frames; base += tile_frames) {
+		const long f0 = base + ((long) w * 32 + lane) * BQ_L;
+		const long rem = frames - f0;
+		const int nv = (rem <= 0) ? 0 : (rem < BQ_L ? (int) rem : BQ_L);
+		// the last valid chunk of this tile hands its end state to the next tile / the next call
+		const bool last_chunk = nv > 0 && (rem <= BQ_L || f0 + BQ_L >= base + tile_frames);
+		double y[BQ_L];
 #pragma unroll
-	for (int g = 0; g < G; ++g) {
-		const bool on = g < ng;
-		const double *cf = coef + (long) (st0 + (on ? g : 0)) * 5 * C + c;
-		// a missing stage (cascade length not a multiple of G) is the identity section
-		c0[g] = on ? cf[0] : 1.0; c1[g] = on ? cf[C] : 0.0; c2[g] = on ? cf[2 * C] : 0.0;
-		c3[g] = on ? cf[3 * C] : 0.0; c4[g] = on ? cf[4 * C] : 0.0;
-		m0[g] = (APPLY && on) ? z0[2 * (st0 + g)] : 0.0;
-		m1[g] = (APPLY && on) ? z0[2 * (st0 + g) + 1] : 0.0;
-	}
+		for (int i = 0; i < BQ_L; ++i) y[i] = (i < nv) ? in[(f0 + i) * C + c] : 0.0;
+
+		for (int st = 0; st < S; ++st) {
+			const double *t = stbl + st * BQ_TBL;
+			const double c0 = t[0], c1 = t[1], c2 = t[2], c3 = t[3], c4 = t[4];
+			M2 P[BQ_NPOW];
 #pragma unroll
-	for (int t = 0; t < BQ_L + G - 1; ++t) {
+			for (int r = 0; r < BQ_NPOW; ++r) P[r] = M2{ t[5 + 4 * r], t[6 + 4 * r], t[7 + 4 * r], t[8 + 4 * r] };
+			// (1) zero-state end state of a FULL chunk as a dot product (a partial last chunk is nobody's predecessor:
+			//     its value is never used; missing samples are zeros)
+			const double *G = t + 5 + 4 * BQ_NPOW;
+			double ex0 = 0.0, ex1 = 0.0, ey0 = 0.0, ey1 = 0.0;
 #pragma unroll
-		for (int g = G - 1; g >= 0; --g) {   // later stages first: stage g reads what stage g-1 wrote one step ago
-			const int i = t - g;
-			if (i >= 0 && i < BQ_L) {
+			for (int i = 0; i < BQ_L; i += 2) {
+				ex0 = fma(G[2 * i], y[i], ex0);
+				ey0 = fma(G[2 * i + 1], y[i], ey0);
+				ex1 = fma(G[2 * i + 2], y[i + 1], ex1);
+				ey1 = fma(G[2 * i + 3], y[i + 1], ey1);
+			}
+			// (2) inclusive scan over the lanes (uniform matrix A^L per chunk)
+			double2 sc = make_double2(ex0 + ex1, ey0 + ey1);
+#pragma unroll
+			for (int r = 0; r < 5; ++r) {
+				const double vx = __shfl_up_sync(0xffffffffu, sc.x, 1 << r), vy = __shfl_up_sync(0xffffffffu, sc.y, 1 << r);
+				if (lane >= (1 << r)) {
+					const double2 u = m2_apply(P[r], make_double2(vx, vy));
+					sc.x += u.x;
+					sc.y += u.y;
+				}
+			}
+			// exclusive: state at the start of this lane's chunk if the warp started from zero
+			double2 z = make_double2(__shfl_up_sync(0xffffffffu, sc.x, 1), __shfl_up_sync(0xffffffffu, sc.y, 1));
+			if (lane == 0) z = make_double2(0.0, 0.0);
+			if (lane == 31) tot[w] = sc;
+			__syncthreads();
+			// (3) carry into this warp, then into this lane
+			double2 cin = carry[st];
+			for (int k = 0; k < w; ++k) {
+				const double2 u = m2_apply(P[5], cin);
+				cin = make_double2(u.x + tot[k].x, u.y + tot[k].y);
+			}
+#pragma unroll
+			for (int r = 0; r < 5; ++r)
+				if ((lane >> r) & 1) cin = m2_apply(P[r], cin);
+			double m0 = z.x + cin.x, m1 = z.y + cin.y;
+			// (4) the real run from the true start state
+#pragma unroll
+			for (int i = 0; i < BQ_L; ++i) {
 				if (i < nv) {
 					const double s = y[i];
-					const double r = c0[g] * s + m0[g];
-					m0[g] = m1[g] + c1[g] * s - c3[g] * r;
-					m1[g] = c2[g] * s - c4[g] * r;
+					const double r = c0 * s + m0;
+					m0 = m1 + c1 * s - c3 * r;
+					m1 = c2 * s - c4 * r;
 					y[i] = r;
 				}
 			}
+			__syncthreads();   // everyone has read tot[] and carry[st]
+			if (last_chunk) carry[st] = make_double2(m0, m1);
 		}
-	}
-	if (store_end) {
-#pragma unroll
-		for (int g = 0; g < G; ++g)
-			if (g < ng) { zend[2 * (st0 + g)] = m0[g]; zend[2 * (st0 + g) + 1] = m1[g]; }
-	}
-}
-
-constexpr int BQ_G = 5;
-
-template <bool APPLY>
-__global__ void __launch_bounds__(128) k_bq_chunks(const double *in, double *out, const double *__restrict__ coef,
-                                                   const double *zin, double *bout, double *zstate,
-                                                   int C, int S, long frames, int n_chunks)
-{
-	const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
-	const int c = (int) (idx % C);
-	const long j = idx / C;
-	if (j >= n_chunks) return;
-	const int D = 2 * S;
-	const long f0 = j * BQ_L;
-	const int nv = (int) ((frames - f0 < BQ_L) ? frames - f0 : BQ_L);
-
-	double y[BQ_L];
-#pragma unroll
-	for (int i = 0; i < BQ_L; ++i) y[i] = (i < nv) ? in[(f0 + i) * C + c] : 0.0;
-
-	const double *z0 = APPLY ? zin + ((long) c * n_chunks + j) * D : nullptr;
-	double *zend = APPLY ? zstate + (long) c * D : bout + ((long) c * n_chunks + j) * D;
-	const bool store_end = APPLY ? (j == n_chunks - 1) : true;
-
-	for (int st0 = 0; st0 < S; st0 += BQ_G)
-		bq_stage_group<APPLY, BQ_G>(y, nv, coef, C, c, st0, (S - st0 < BQ_G) ? S - st0 : BQ_G, z0, zend, store_end);
-
-	if (APPLY) {
 #pragma unroll
 		for (int i = 0; i < BQ_L; ++i)
 			if (i < nv) out[(f0 + i) * C + c] = y[i];
+		__syncthreads();   // carry[] complete before the next tile reads it
 	}
-}
-
-// Chunk start states for one channel per CTA.  With P_k = M_c^k (k = 1..8, M_c = A_c^L the one-chunk
-// transition) the serial recurrence z_{j+1} = M z_j + b_j over all chunks is cut into groups of 8 chunks:
-//   (1) every warp scans ITS group from a zero state: u_{k+1} = P_1 u_k + b_{8G+k}   (7 serial steps, 16 groups in parallel)
-//   (2) warp 0 carries the group totals across groups: Z_{G+1} = P_8 Z_G + t_G       (one serial step per group)
-//   (3) every warp rebuilds its chunks' true start states: z_{8G+k} = u_k + P_k Z_G  (independent)
-// so the serial depth for 128 chunks is 7 + 16 + 1 matrix-vector products instead of 128.  Lane d owns state
-// component d (D <= 32); the vectors live in shared memory.
-constexpr int BQ_GRP = 8;
-constexpr int BQ_SCAN_WARPS = 16;
-
-// sum_e Pt[e][lane] * v[e] + init, Pt = transposed matrix in shared memory (lane-contiguous rows), four partial sums
-__device__ __forceinline__ double bq_col_dot(const double *Pt, int D, int lane, const double *v, double init)
-{
-	double a0 = init, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-	int e = 0;
-	for (; e + 4 <= D; e += 4) {
-		a0 = fma(Pt[e * D + lane], v[e], a0);
-		a1 = fma(Pt[(e + 1) * D + lane], v[e + 1], a1);
-		a2 = fma(Pt[(e + 2) * D + lane], v[e + 2], a2);
-		a3 = fma(Pt[(e + 3) * D + lane], v[e + 3], a3);
-	}
-	for (; e < D; ++e) a0 = fma(Pt[e * D + lane], v[e], a0);
-	return (a0 + a1) + (a2 + a3);
-}
-
-__global__ void __launch_bounds__(32 * BQ_SCAN_WARPS) k_bq_scan(const double *__restrict__ Pw, const double *__restrict__ b, double *__restrict__ zin,
-                                                                const double *__restrict__ zstate, int C, int D, int n_chunks)
-{
-	extern __shared__ double dyn[];
-	double *Pt = dyn;                                              // [BQ_GRP][D][D], P_k transposed: Pt[k-1][e][d]
-	double (*u)[32] = reinterpret_cast<double (*)[32]>(Pt + BQ_GRP * D * D + ((BQ_GRP * D * D) & 1));   // [WARPS*GRP][32]
-	double (*tot)[32] = u + BQ_SCAN_WARPS * BQ_GRP;                // [WARPS][32]
-	double (*Z)[32] = tot + BQ_SCAN_WARPS;                         // [WARPS+1][32]
-	const int c = blockIdx.x;
-	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const double *bc = b + (long) c * n_chunks * D;
-	double *zc = zin + (long) c * n_chunks * D;
-	const bool on = lane < D;
-	{
-		const double *P = Pw + (long) c * BQ_GRP * D * D;
-		for (int i = threadIdx.x; i < BQ_GRP * D * D; i += blockDim.x) Pt[i] = P[i];
-	}
-	if (w == 0) Z[0][lane] = on ? zstate[(long) c * D + lane] : 0.0;
-	__syncthreads();
-
-	const int super = BQ_SCAN_WARPS * BQ_GRP;           // chunks per pass of the CTA
-	for (int base = 0; base < n_chunks; base += super) {
-		const int n_here = (n_chunks - base < super) ? n_chunks - base : super;
-		const int n_groups = (n_here + BQ_GRP - 1) / BQ_GRP;
-		// (1) group-local scans from zero
-		if (w < n_groups) {
-			double bk[BQ_GRP];
-#pragma unroll
-			for (int k = 0; k < BQ_GRP; ++k) {
-				const int j = w * BQ_GRP + k;
-				bk[k] = (on && j < n_here) ? bc[(long) (base + j) * D + lane] : 0.0;
-			}
-			double uk = 0.0;
-#pragma unroll
-			for (int k = 0; k < BQ_GRP; ++k) {
-				const int j = w * BQ_GRP + k;
-				u[j][lane] = uk;
-				__syncwarp();
-				if (j < n_here && on) uk = bq_col_dot(Pt, D, lane, u[j], bk[k]);
-			}
-			tot[w][lane] = uk;
-		}
-		__syncthreads();
-		// (2) carry across the groups of this super-block
-		if (w == 0) {
-			const double *p8 = Pt + (BQ_GRP - 1) * D * D;
-			for (int G = 0; G < n_groups; ++G) {
-				const double z = on ? bq_col_dot(p8, D, lane, Z[G], tot[G][lane]) : 0.0;
-				Z[G + 1][lane] = z;
-				__syncwarp();
-			}
-		}
-		__syncthreads();
-		// (3) true chunk start states
-		if (w < n_groups && on) {
-#pragma unroll
-			for (int k = 0; k < BQ_GRP; ++k) {
-				const int j = w * BQ_GRP + k;
-				if (j < n_here) {
-					double z = u[j][lane];
-					if (k == 0) z += Z[w][lane];
-					else z = bq_col_dot(Pt + (k - 1) * D * D, D, lane, Z[w], z);
-					zc[(long) (base + j) * D + lane] = z;
-				}
-			}
-		}
-		__syncthreads();
-		// the next super-block starts where this one ended -- only if it was full (otherwise we are done)
-		if (w == 0 && n_here == super) Z[0][lane] = Z[n_groups][lane];
-		__syncthreads();
+	if (threadIdx.x < S) {
+		zstate[((long) c * S + threadIdx.x) * 2] = carry[threadIdx.x].x;
+		zstate[((long) c * S + threadIdx.x) * 2 + 1] = carry[threadIdx.x].y;
 	}
 }
 
 struct BiquadOp : Op {
-	int S = 0, D = 0;
+	int S = 0;
 	std::vector<double> h_coefs;   // [S][C][5] as handed in (kept so neighbouring cascades can be fused)
-	double *d_coef = nullptr, *d_M = nullptr, *d_zstate = nullptr, *d_b = nullptr, *d_zin = nullptr;
-	long chunk_cap = 0;
+	double *d_tbl = nullptr, *d_zstate = nullptr;
 
 	const char *name() const override { return "biquad"; }
-	~BiquadOp() override { dev_free(d_coef); dev_free(d_M); dev_free(d_zstate); dev_free(d_b); dev_free(d_zin); }
+	std::string describe() const override
+	{
+		char buf[96];
+		snprintf(buf, sizeof(buf), "{\"op\":\"biquad\",\"stages\":%d}", S);
+		return buf;
+	}
+	~BiquadOp() override { dev_free(d_tbl); dev_free(d_zstate); }
 
 	void reset(cudaStream_t st) override
 	{
-		cudaMemsetAsync(d_zstate, 0, (size_t) channels * D * sizeof(double), st);
+		cudaMemsetAsync(d_zstate, 0, (size_t) channels * S * 2 * sizeof(double), st);
 	}
 
 	long run(long frames, const double *in, double *out, cudaStream_t st) override
 	{
-		return run_piece(frames, in, out, st);
-	}
-
-	long run_piece(long frames, const double *in, double *out, cudaStream_t st)
-	{
 		if (frames <= 0) return 0;
-		const int C = channels;
-		const long n_chunks = (frames + BQ_L - 1) / BQ_L;
-		const long threads = n_chunks * C;
 		ProfScope prof("biquad", st);
-		if (n_chunks == 1) {
-			// the chunk starts from the carried state itself: zin == zstate (layout [c][1][D])
-			LAUNCH(k_bq_chunks<true>, ceil_div(threads, 128), 128, 0, st, in, out, d_coef, d_zstate, nullptr, d_zstate, C, S, frames, 1);
-			return frames;
-		}
-		if (n_chunks > chunk_cap) {
-			dev_free(d_b); dev_free(d_zin);
-			d_b = dev_alloc<double>((size_t) n_chunks * C * D, false);
-			d_zin = dev_alloc<double>((size_t) n_chunks * C * D, false);
-			if (!d_b || !d_zin) return -1;
-			chunk_cap = n_chunks;
-		}
-		{
-			ProfScope p1("bq_local", st);
-			LAUNCH(k_bq_chunks<false>, ceil_div(threads, 128), 128, 0, st, in, nullptr, d_coef, nullptr, d_b, nullptr, C, S, frames, (int) n_chunks);
-		}
-		{
-			ProfScope p2("bq_scan", st);
-			const size_t smem = ((size_t) BQ_GRP * D * D + 1 + (size_t) (BQ_SCAN_WARPS * BQ_GRP + 2 * BQ_SCAN_WARPS + 1) * 32) * sizeof(double);
-			static std::atomic<int> configured[64];
-			int dev = 0;
-			cudaGetDevice(&dev);
-			if (!configured[dev & 63].load()) {
-				const size_t smem_max = ((size_t) BQ_GRP * 4 * BQ_MAX_STAGES * BQ_MAX_STAGES + 1 + (size_t) (BQ_SCAN_WARPS * BQ_GRP + 2 * BQ_SCAN_WARPS + 1) * 32) * sizeof(double);
-				CUDA_TRY(cudaFuncSetAttribute(k_bq_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max), return -1);
-				configured[dev & 63].store(1);
-			}
-			LAUNCH(k_bq_scan, C, 32 * BQ_SCAN_WARPS, smem, st, d_M, d_b, d_zin, d_zstate, C, D, (int) n_chunks);
-		}
-		{
-			ProfScope p3("bq_apply", st);
-			LAUNCH(k_bq_chunks<true>, ceil_div(threads, 128), 128, 0, st, in, out, d_coef, d_zin, nullptr, d_zstate, C, S, frames, (int) n_chunks);
-		}
+		LAUNCH(k_bq_cascade, channels, 32 * BQ_WARPS, (size_t) S * BQ_TBL * sizeof(double), st, in, out, d_tbl, d_zstate, channels, S, frames);
 		return frames;
 	}
 };
-
-// zero-input step of the cascade (same arithmetic as biquad.h:79-81 with s = 0 at stage 0)
-static void cascade_zero_input_step(int S, const double *cf /*[S][5]*/, long double *z /*[2S]*/)
-{
-	long double s = 0.0L;
-	for (int st = 0; st < S; ++st) {
-		const long double c0 = cf[st * 5 + 0], c1 = cf[st * 5 + 1], c2 = cf[st * 5 + 2], c3 = cf[st * 5 + 3], c4 = cf[st * 5 + 4];
-		const long double r = c0 * s + z[2 * st];
-		z[2 * st] = z[2 * st + 1] + c1 * s - c3 * r;
-		z[2 * st + 1] = c2 * s - c4 * r;
-		s = r;
-	}
-}
 
 Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 {
@@ -282,41 +169,50 @@ Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 		return nullptr;
 	}
 	std::unique_ptr<BiquadOp> op(new BiquadOp());
-	const int C = slab_channels, S = n_stages, D = 2 * n_stages;
-	op->channels = C; op->fs_in = op->fs_out = fs; op->S = S; op->D = D;
+	const int C = slab_channels, S = n_stages;
+	op->channels = C; op->fs_in = op->fs_out = fs; op->S = S;
 	op->h_coefs.assign(coefs, coefs + (size_t) S * C * 5);
 
-	// coefs arrive as [stage][channel][5]; device wants [stage][5][channel]
-	std::vector<double> dev_coef((size_t) S * 5 * C), M((size_t) C * BQ_GRP * D * D);
-	std::vector<double> cf((size_t) S * 5);
-	std::vector<long double> z(D);
+	// coefs arrive as [stage][channel][5]; the kernel wants one contiguous table per channel (a CTA reads one channel)
+	std::vector<double> tbl((size_t) C * S * BQ_TBL);
 	for (int c = 0; c < C; ++c) {
-		for (int st = 0; st < S; ++st)
-			for (int k = 0; k < 5; ++k) {
-				const double v = coefs[((size_t) st * C + c) * 5 + k];
-				dev_coef[((size_t) st * 5 + k) * C + c] = v;
-				cf[st * 5 + k] = v;
+		for (int st = 0; st < S; ++st) {
+			const double *cf = &coefs[((size_t) st * C + c) * 5];
+			double *t = &tbl[((size_t) c * S + st) * BQ_TBL];
+			for (int k = 0; k < 5; ++k) t[k] = cf[k];
+			// A = [[-c3, 1], [-c4, 0]], B = (c1 - c3 c0, c2 - c4 c0): z' = A z + B s   (biquad.h:79-81 with r = c0 s + m0)
+			const long double A[4] = { -(long double) cf[3], 1.0L, -(long double) cf[4], 0.0L };
+			const long double Bv[2] = { (long double) cf[1] - (long double) cf[3] * cf[0], (long double) cf[2] - (long double) cf[4] * cf[0] };
+			// G[i] = A^(L-1-i) B, i = L-1 .. 0, and A^L on the way
+			long double g[2] = { Bv[0], Bv[1] };
+			for (int i = BQ_L - 1; i >= 0; --i) {
+				t[5 + 4 * BQ_NPOW + 2 * i] = (double) g[0];
+				t[5 + 4 * BQ_NPOW + 2 * i + 1] = (double) g[1];
+				const long double n0 = A[0] * g[0] + A[1] * g[1], n1 = A[2] * g[0] + A[3] * g[1];
+				g[0] = n0; g[1] = n1;
 			}
-		// column e of P_k = A_c^(k L) e_e, k = 1..BQ_GRP: iterate the zero-input step of the cascade
-		for (int e = 0; e < D; ++e) {
-			for (int d = 0; d < D; ++d) z[d] = (d == e) ? 1.0L : 0.0L;
-			for (int k = 1; k <= BQ_GRP; ++k) {
-				for (int i = 0; i < BQ_L; ++i) cascade_zero_input_step(S, cf.data(), z.data());
-				for (int d = 0; d < D; ++d) M[(((size_t) c * BQ_GRP + (k - 1)) * D + e) * D + d] = (double) z[d];   // transposed: [e][d]
+			long double a[4] = { 1.0L, 0.0L, 0.0L, 1.0L };
+			for (int i = 0; i < BQ_L; ++i) {
+				const long double u[4] = { A[0] * a[0] + A[1] * a[2], A[0] * a[1] + A[1] * a[3], A[2] * a[0] + A[3] * a[2], A[2] * a[1] + A[3] * a[3] };
+				for (int k = 0; k < 4; ++k) a[k] = u[k];
+			}
+			// A^(L 2^r) by repeated squaring
+			for (int r = 0; r < BQ_NPOW; ++r) {
+				for (int k = 0; k < 4; ++k) t[5 + 4 * r + k] = (double) a[k];
+				const long double u[4] = { a[0] * a[0] + a[1] * a[2], a[0] * a[1] + a[1] * a[3], a[2] * a[0] + a[3] * a[2], a[2] * a[1] + a[3] * a[3] };
+				for (int k = 0; k < 4; ++k) a[k] = u[k];
 			}
 		}
 	}
-	op->d_coef = dev_alloc<double>(dev_coef.size(), false);
-	op->d_M = dev_alloc<double>(M.size(), false);
-	op->d_zstate = dev_alloc<double>((size_t) C * D, true);
-	if (!op->d_coef || !op->d_M || !op->d_zstate) return nullptr;
-	CUDA_TRY(cudaMemcpy(op->d_coef, dev_coef.data(), dev_coef.size() * sizeof(double), cudaMemcpyHostToDevice), return nullptr);
-	CUDA_TRY(cudaMemcpy(op->d_M, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice), return nullptr);
+	op->d_tbl = dev_alloc<double>(tbl.size(), false);
+	op->d_zstate = dev_alloc<double>((size_t) C * S * 2, true);
+	if (!op->d_tbl || !op->d_zstate) return nullptr;
+	CUDA_TRY(cudaMemcpy(op->d_tbl, tbl.data(), tbl.size() * sizeof(double), cudaMemcpyHostToDevice), return nullptr);
 	return op.release();
 }
 
-// Two adjacent cascades over the same slab become one operator (one pass over the block) when
-// the state still fits one lane per component.  Only legal before the first run()/after reset.
+// Two adjacent cascades over the same slab become one operator (one pass over the block).
+// Only legal before the first run()/after reset.
 Op *fuse_biquad_ops(Op *a, Op *b)
 {
 	BiquadOp *x = dynamic_cast<BiquadOp *>(a), *y = dynamic_cast<BiquadOp *>(b);

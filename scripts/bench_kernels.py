@@ -18,13 +18,18 @@ def timed(chain, blocks, d_out, F, steps=200, warm=5, names=()):
     for i in range(warm):
         chain.run_device(0, F, blocks[i % len(blocks)].data_ptr(), d_out.data_ptr(), st)
     torch.cuda.synchronize()
-    for n in names: dsp_b200.profile_read(n)
-    dsp_b200.profile_enable(True)
+    # throughput: plain loop, CUDA events on the launching stream around all of it
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         chain.run_device(0, F, blocks[i % len(blocks)].data_ptr(), d_out.data_ptr(), st)
     e1.record(); torch.cuda.synchronize()
+    # per-kernel durations: a second, instrumented pass
+    for n in names: dsp_b200.profile_read(n)
+    dsp_b200.profile_enable(True)
+    for i in range(steps):
+        chain.run_device(0, F, blocks[i % len(blocks)].data_ptr(), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
     dsp_b200.profile_enable(False)
     prof = {n: dsp_b200.profile_read(n) for n in names}
     return e0.elapsed_time(e1) / steps, prof
@@ -36,11 +41,11 @@ coefs = np.array([dsp_b200.biquad_design(13, fs, f[i], 1.4, g[i]) for i in range
 ch = dsp_b200.Chain(fs, C).add_biquad(coefs)
 blocks = [torch.from_numpy(bench.make_block(F, C, i)).cuda() for i in range(16)]   # 128 MB of distinct input > L2? no: 8 MB each
 d_out = torch.empty((F, C), dtype=torch.float64, device="cuda")
-ms, prof = timed(ch, blocks, d_out, F, names=("biquad", "bq_local", "bq_scan", "bq_apply"))
+ms, prof = timed(ch, blocks, d_out, F, names=("biquad",))
 sps = C * F / (ms * 1e-3)
 out["C2_biquad10_256ch"] = {"ms_per_block": ms, "Msamples_per_s": sps / 1e6, "bytes_per_sample": 16,
                            "hbm_GBs": sps * 16 / 1e9, "hbm_frac_of_measured": sps * 16 / 1e9 / peak,
-                           "kernel_us": {k: v[0] / max(v[1], 1) * 1e3 for k, v in prof.items()}, "fp64_flops_per_sample_min": 90, "note": "3 launches per block (zero-state chunks, scan, apply)"}
+                           "kernel_us": {k: v[0] / max(v[1], 1) * 1e3 for k, v in prof.items()}, "fp64_flops_per_sample_min": 90, "note": "one launch per block (k_bq_cascade)"}
 ch.close()
 
 # C4: resample 44100 -> 48000, 1024 ch (single GPU form)
