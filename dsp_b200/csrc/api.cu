@@ -175,12 +175,15 @@ struct Shard {
 	std::vector<std::unique_ptr<Op>> ops;
 	double *buf[4] = { nullptr, nullptr, nullptr, nullptr };   // io-in, io-out/scratch, scratch, zeros
 	size_t cap = 0;   // doubles per buffer
+	static constexpr int DONE_RING = 8;
+	cudaEvent_t done[DONE_RING] = {};   // completion markers of submitted host blocks (ticket % DONE_RING)
 
 	~Shard()
 	{
 		cudaSetDevice(device);
 		ops.clear();
 		for (double *b : buf) dev_free(b);
+		for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
 		if (stream) cudaStreamDestroy(stream);
 	}
 
@@ -262,6 +265,7 @@ struct dspb200_chain {
 	std::vector<std::unique_ptr<Shard>> shards;
 	std::vector<std::pair<void *, size_t>> registered;    // host ranges pinned by us
 	bool pin_host = false;
+	unsigned long long ticket = 0;   // blocks submitted so far (dspb200_chain_submit_host)
 
 	~dspb200_chain()
 	{
@@ -566,7 +570,7 @@ static int copy_slab(const Shard &s, int C, long frames, double *dev, const doub
 	return 0;
 }
 
-long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, double *out)
+long dspb200_chain_submit_host(dspb200_chain *c, long frames, const double *in, double *out, unsigned long long *ticket)
 {
 	if (!c || !in || !out) return -1;
 	if (frames < 1) return 0;
@@ -575,7 +579,7 @@ long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, dou
 	maybe_pin(c, in, (size_t) frames * C * sizeof(double));
 	if (out != in) maybe_pin(c, out, (size_t) ((max_out > frames) ? max_out : frames) * C * sizeof(double));
 	long result = -1;
-	bool failed = false;
+	const unsigned long long t = ++c->ticket;
 	FOR_EACH_SHARD(c, s) {
 		CUDA_TRY(cudaSetDevice(s->device), return -1);
 		if (s->ensure_cap(frames)) return -1;
@@ -584,15 +588,44 @@ long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, dou
 		for (auto &op : s->ops) rate_change |= !op->inplace_ok;
 		double *dst = rate_change ? s->buf[3] : s->buf[0];
 		const long f = s->run_ops(0, frames, s->buf[0], dst, true, s->stream);
-		if (f < 0) { failed = true; break; }
+		if (f < 0) return -1;
 		if (copy_slab(*s, C, f, dst, nullptr, out)) return -1;
+		if (ticket) {
+			cudaEvent_t &ev = s->done[t % Shard::DONE_RING];
+			if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), return -1);
+			CUDA_TRY(cudaEventRecord(ev, s->stream), return -1);
+		}
 		result = f;
 	}
+	if (ticket) *ticket = t;
+	return result;
+}
+
+int dspb200_chain_wait(dspb200_chain *c, unsigned long long ticket)
+{
+	if (!c || ticket == 0 || ticket > c->ticket) return -1;
+	// A marker is reused every DONE_RING submissions; each shard's stream is in order, so waiting
+	// on the newer marker that replaced an old ticket's also covers the old ticket.
+	FOR_EACH_SHARD(c, s) {
+		cudaEvent_t ev = s->done[ticket % Shard::DONE_RING];
+		cudaSetDevice(s->device);
+		if (ev) CUDA_TRY(cudaEventSynchronize(ev), return -1);
+		else CUDA_TRY(cudaStreamSynchronize(s->stream), return -1);
+	}
+	return 0;
+}
+
+long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, double *out)
+{
+	if (!c || !in || !out) return -1;
+	if (frames < 1) return 0;
+	const long result = dspb200_chain_submit_host(c, frames, in, out, nullptr);
+	// also after a failed submit: nothing of this call may still be in flight when we return
 	FOR_EACH_SHARD(c, s) {
 		cudaSetDevice(s->device);
 		CUDA_TRY(cudaStreamSynchronize(s->stream), return -1);
 	}
-	return failed ? -1 : result;
+	return result;
 }
 
 long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const double *d_in, double *d_out, void *stream)

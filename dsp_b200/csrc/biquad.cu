@@ -7,33 +7,38 @@
 // Per stage (biquad.h:79-81):   r = c0 s + m0;  m0' = m1 + c1 s - c3 r;  m1' = c2 s - c4 r
 // i.e. the state z = (m0, m1) follows z' = A z + B s with A = [[-c3, 1], [-c4, 0]] (zero-input step).
 // The per-sample recurrence is parallelised along TIME as an associative scan over these affine maps:
-//   * a CTA owns one channel; its 128 threads own 128 consecutive chunks of L = 32 frames (lanes run
-//     along time), the chunk's samples live in registers through all S stages;
+//   * a CTA owns two adjacent channels and a tile of 4096 frames; a lane owns one chunk of L = 16 frames of one
+//     channel (a warp = 16 consecutive chunks x 2 channels, channel fastest), the chunk's samples live in
+//     registers through all S stages;
 //   * per stage: (1) every lane needs the end state e its chunk would reach from a ZERO state; that is the
-//     dot product e = sum_i A^(L-1-i) B s_i of the chunk with a per-stage table (64 independent FMAs instead of
-//     a serial recurrence; table built on the host in long double); (2) warp-level inclusive scan of the states by shuffles -- all chunks share the matrix
-//     A^L, so round r is  s += A^(L 2^r) shfl_up(s, 2^r)  with the five powers taken on the host in long
-//     double; (3) warp totals are chained through shared memory with A^(32 L), every lane turns the
-//     carry-in of its warp into its own start state with the binary expansion of its lane index;
-//     (4) the lane re-runs the reference's own recurrence from that TRUE start state -- so every output
-//     sample is produced by exactly the reference's arithmetic, started from a state that differs from the
-//     sequential one only by rounding in the scan (|eig A| < 1);
-//   * longer calls loop over tiles of 128 chunks, carrying the per-stage state through shared memory.
+//     dot product e = sum_i A^(L-1-i) B s_i of the chunk with a per-stage table (2 L independent FMAs instead
+//     of a serial recurrence; table built on the host in long double); (2) warp-level inclusive scan of the
+//     states by shuffles -- all chunks share the matrix A^L, so round r is  s += A^(L 2^r) shfl_up(s, 2 * 2^r)
+//     with the powers taken on the host in long double; (3) warp totals are chained through shared memory
+//     with A^(16 L), every lane turns the carry-in of its warp into its own start state with the binary
+//     expansion of its chunk index; (4) the lane re-runs the reference's own recurrence from that TRUE start
+//     state -- so every output sample is produced by exactly the reference's arithmetic, started from a
+//     state that differs from the sequential one only by rounding in the scan (|eig A| < 1);
+//   * longer calls loop over tiles, carrying the per-stage state through shared memory.
 // A stage that does not act on a channel carries the identity section {1,0,0,0,0}.
-// Global accesses are 8-byte loads/stores strided by the channel count (a lane's 32 frames); the four
-// channels sharing each 32-byte sector are read by neighbouring CTAs at about the same time, so HBM
-// sees every sector once (L2 absorbs the rest).  Algorithmic bytes: 16 per sample.
+// Global accesses: one load instruction of a warp touches 16 rows (frames) and uses 16 contiguous bytes of
+// each -- half of every 32-byte sector, the neighbouring CTA uses the other half at about the same time, so
+// HBM sees every sector once (L2 absorbs the rest).  (One channel per CTA = 32 sectors per request, measured
+// 16.4 us for a 1-stage pass over a config-2 block against 10.3 us for pairs; four channels per CTA halves
+// the grid and loses more than it gains at 256 channels.)  Algorithmic bytes: 16 per sample.
 #include "common.cuh"
 #include "ops.h"
 
 namespace dspb200 {
 
 constexpr int BQ_L = 16;           // frames per lane
-constexpr int BQ_WARPS = 8;        // warps per CTA: 256 chunks = 4096 frames per tile
 constexpr int BQ_MAX_STAGES = 16;  // stages fused into one operator
-constexpr int BQ_NPOW = 6;         // A^(L 2^r), r = 0..5 (r = 5: one warp's span)
-// per channel and stage: 5 coefficients, BQ_NPOW 2x2 matrices, and G[i] = A^(L-1-i) B (2 x L), contiguous
-constexpr int BQ_TBL = 5 + 4 * BQ_NPOW + 2 * BQ_L;
+constexpr int BQ_NPOW = 6;         // A^(L 2^r), r = 0..5
+// per channel and stage: 5 coefficients (+1 pad), BQ_NPOW 2x2 matrices, and G[i] = A^(L-1-i) B (2 x L), contiguous;
+// every piece starts on a 16-byte boundary so that the kernel reads the table with 128-bit shared loads
+constexpr int BQ_OFF_P = 6, BQ_OFF_G = BQ_OFF_P + 4 * BQ_NPOW;
+constexpr int BQ_TBL = BQ_OFF_G + 2 * BQ_L;
+static_assert(BQ_TBL % 2 == 0 && BQ_OFF_G % 2 == 0, "table pieces must stay 16-byte aligned");
 
 struct M2 { double a, b, c, d; };  // [[a, b], [c, d]]
 
@@ -42,96 +47,134 @@ __device__ __forceinline__ double2 m2_apply(const M2 &m, double2 v)
 	return make_double2(fma(m.a, v.x, m.b * v.y), fma(m.c, v.x, m.d * v.y));
 }
 
-// tbl: [C][S][BQ_TBL] (see BQ_TBL), zstate: [C][S][2]
-__global__ void __launch_bounds__(32 * BQ_WARPS) k_bq_cascade(const double *in, double *out, const double *__restrict__ tbl,
-                                                             double *zstate, int C, int S, long frames)
-{
-	__shared__ double2 tot[BQ_WARPS];
-	__shared__ double2 carry[BQ_MAX_STAGES];
-	extern __shared__ double stbl[];   // [S][BQ_TBL]: this channel's tables (every lane reads the same entries: broadcasts)
-	const int c = blockIdx.x;
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	for (int i = threadIdx.x; i < S * BQ_TBL; i += blockDim.x) stbl[i] = tbl[(long) c * S * BQ_TBL + i];
-	if (threadIdx.x < S) carry[threadIdx.x] = make_double2(zstate[((long) c * S + threadIdx.x) * 2], zstate[((long) c * S + threadIdx.x) * 2 + 1]);
-	__syncthreads();
+// CH adjacent channels share a CTA; a warp's lanes are (32 / CH consecutive chunks) x (CH channels), channel
+// fastest, so that one load instruction touches 32 / CH rows and uses CH x 8 contiguous bytes of each.
+template <int CH>
+struct BqCfg {
+	static_assert(CH == 1 || CH == 2 || CH == 4, "1, 2 or 4 channels per CTA");
+	static constexpr int CPW = 32 / CH;                         // chunks per warp
+	static constexpr int LOGW = (CH == 1) ? 5 : (CH == 2) ? 4 : 3;
+	static constexpr int WARPS = (CH == 1) ? 8 : 16;
+	static constexpr int THREADS = 32 * WARPS;
+	static constexpr long TILE = (long) BQ_L * CPW * WARPS;     // frames per tile
+};
 
-	const long tile_frames = (long) BQ_L * 32 * BQ_WARPS;
-	for (long base = 0; base < frames; base += tile_frames) {
-		const long f0 = base + ((long) w * 32 + lane) * BQ_L;
+// tbl: [C][S][BQ_TBL] (see BQ_TBL), zstate: [C][S][2]
+template <int CH>
+__global__ void __launch_bounds__(BqCfg<CH>::THREADS) k_bq_cascade(const double *in, double *out, const double *__restrict__ tbl,
+                                                                  double *zstate, int C, int S, long frames)
+{
+	using Cfg = BqCfg<CH>;
+	constexpr int LOGW = Cfg::LOGW;
+	__shared__ double2 tot[Cfg::WARPS][CH];
+	__shared__ double2 carry[BQ_MAX_STAGES][CH];
+	extern __shared__ __align__(16) double stbl[];   // [CH][S][BQ_TBL]: these channels' tables
+	const int c0 = blockIdx.x * CH;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int ch = lane & (CH - 1), jl = lane / CH;     // channel within the CTA, chunk within the warp
+	const int c = c0 + ch;
+	const bool have = c < C;
+	const int nch = (C - c0 < CH) ? C - c0 : CH;
+	for (int i = threadIdx.x; i < nch * S * BQ_TBL; i += blockDim.x) stbl[i] = tbl[(long) c0 * S * BQ_TBL + i];
+	if (threadIdx.x < S * CH) {
+		const int st = threadIdx.x / CH, k = threadIdx.x % CH;
+		carry[st][k] = (k < nch) ? make_double2(zstate[((long) (c0 + k) * S + st) * 2], zstate[((long) (c0 + k) * S + st) * 2 + 1])
+		                         : make_double2(0.0, 0.0);
+	}
+	__syncthreads();
+	const double *mytbl = stbl + (have ? ch : 0) * S * BQ_TBL;
+
+	for (long base = 0; base < frames; base += Cfg::TILE) {
+		const long f0 = base + ((long) w * Cfg::CPW + jl) * BQ_L;
 		const long rem = frames - f0;
-		const int nv = (rem <= 0) ? 0 : (rem < BQ_L ? (int) rem : BQ_L);
+		const int nv = (rem <= 0 || !have) ? 0 : (rem < BQ_L ? (int) rem : BQ_L);
 		// the last valid chunk of this tile hands its end state to the next tile / the next call
-		const bool last_chunk = nv > 0 && (rem <= BQ_L || f0 + BQ_L >= base + tile_frames);
+		const bool last_chunk = nv > 0 && (rem <= BQ_L || f0 + BQ_L >= base + Cfg::TILE);
 		double y[BQ_L];
 #pragma unroll
 		for (int i = 0; i < BQ_L; ++i) y[i] = (i < nv) ? in[(f0 + i) * C + c] : 0.0;
 
 		for (int st = 0; st < S; ++st) {
-			const double *t = stbl + st * BQ_TBL;
-			const double c0 = t[0], c1 = t[1], c2 = t[2], c3 = t[3], c4 = t[4];
-			M2 P[BQ_NPOW];
+			const double2 *t = reinterpret_cast<const double2 *>(mytbl + st * BQ_TBL);
+			const double2 t0 = t[0], t1 = t[1], t2 = t[2];
+			const double c0_ = t0.x, c1 = t0.y, c2 = t1.x, c3 = t1.y, c4 = t2.x;
+			M2 P[LOGW + 1];
 #pragma unroll
-			for (int r = 0; r < BQ_NPOW; ++r) P[r] = M2{ t[5 + 4 * r], t[6 + 4 * r], t[7 + 4 * r], t[8 + 4 * r] };
+			for (int r = 0; r <= LOGW; ++r) {
+				const double2 lo = t[BQ_OFF_P / 2 + 2 * r], hi = t[BQ_OFF_P / 2 + 2 * r + 1];
+				P[r] = M2{ lo.x, lo.y, hi.x, hi.y };
+			}
 			// (1) zero-state end state of a FULL chunk as a dot product (a partial last chunk is nobody's predecessor:
 			//     its value is never used; missing samples are zeros)
-			const double *G = t + 5 + 4 * BQ_NPOW;
+			const double2 *G = t + BQ_OFF_G / 2;
 			double ex0 = 0.0, ex1 = 0.0, ey0 = 0.0, ey1 = 0.0;
 #pragma unroll
 			for (int i = 0; i < BQ_L; i += 2) {
-				ex0 = fma(G[2 * i], y[i], ex0);
-				ey0 = fma(G[2 * i + 1], y[i], ey0);
-				ex1 = fma(G[2 * i + 2], y[i + 1], ex1);
-				ey1 = fma(G[2 * i + 3], y[i + 1], ey1);
+				const double2 g0 = G[i], g1 = G[i + 1];
+				ex0 = fma(g0.x, y[i], ex0);
+				ey0 = fma(g0.y, y[i], ey0);
+				ex1 = fma(g1.x, y[i + 1], ex1);
+				ey1 = fma(g1.y, y[i + 1], ey1);
 			}
-			// (2) inclusive scan over the lanes (uniform matrix A^L per chunk)
+			// (2) inclusive scan over the chunks of this warp (uniform matrix A^L per chunk); lanes CH apart
 			double2 sc = make_double2(ex0 + ex1, ey0 + ey1);
 #pragma unroll
-			for (int r = 0; r < 5; ++r) {
-				const double vx = __shfl_up_sync(0xffffffffu, sc.x, 1 << r), vy = __shfl_up_sync(0xffffffffu, sc.y, 1 << r);
-				if (lane >= (1 << r)) {
+			for (int r = 0; r < LOGW; ++r) {
+				const double vx = __shfl_up_sync(0xffffffffu, sc.x, CH << r), vy = __shfl_up_sync(0xffffffffu, sc.y, CH << r);
+				if (jl >= (1 << r)) {
 					const double2 u = m2_apply(P[r], make_double2(vx, vy));
 					sc.x += u.x;
 					sc.y += u.y;
 				}
 			}
 			// exclusive: state at the start of this lane's chunk if the warp started from zero
-			double2 z = make_double2(__shfl_up_sync(0xffffffffu, sc.x, 1), __shfl_up_sync(0xffffffffu, sc.y, 1));
-			if (lane == 0) z = make_double2(0.0, 0.0);
-			if (lane == 31) tot[w] = sc;
+			double2 z = make_double2(__shfl_up_sync(0xffffffffu, sc.x, CH), __shfl_up_sync(0xffffffffu, sc.y, CH));
+			if (jl == 0) z = make_double2(0.0, 0.0);
+			if (jl == Cfg::CPW - 1) tot[w][ch] = sc;
 			__syncthreads();
 			// (3) carry into this warp, then into this lane
-			double2 cin = carry[st];
+			double2 cin = carry[st][ch];
 			for (int k = 0; k < w; ++k) {
-				const double2 u = m2_apply(P[5], cin);
-				cin = make_double2(u.x + tot[k].x, u.y + tot[k].y);
+				const double2 u = m2_apply(P[LOGW], cin);
+				cin = make_double2(u.x + tot[k][ch].x, u.y + tot[k][ch].y);
 			}
 #pragma unroll
-			for (int r = 0; r < 5; ++r)
-				if ((lane >> r) & 1) cin = m2_apply(P[r], cin);
+			for (int r = 0; r < LOGW; ++r)
+				if ((jl >> r) & 1) cin = m2_apply(P[r], cin);
 			double m0 = z.x + cin.x, m1 = z.y + cin.y;
 			// (4) the real run from the true start state
 #pragma unroll
 			for (int i = 0; i < BQ_L; ++i) {
 				if (i < nv) {
 					const double s = y[i];
-					const double r = c0 * s + m0;
+					const double r = c0_ * s + m0;
 					m0 = m1 + c1 * s - c3 * r;
 					m1 = c2 * s - c4 * r;
 					y[i] = r;
 				}
 			}
 			__syncthreads();   // everyone has read tot[] and carry[st]
-			if (last_chunk) carry[st] = make_double2(m0, m1);
+			if (last_chunk) carry[st][ch] = make_double2(m0, m1);
 		}
 #pragma unroll
 		for (int i = 0; i < BQ_L; ++i)
 			if (i < nv) out[(f0 + i) * C + c] = y[i];
 		__syncthreads();   // carry[] complete before the next tile reads it
 	}
-	if (threadIdx.x < S) {
-		zstate[((long) c * S + threadIdx.x) * 2] = carry[threadIdx.x].x;
-		zstate[((long) c * S + threadIdx.x) * 2 + 1] = carry[threadIdx.x].y;
+	if (threadIdx.x < S * CH) {
+		const int st = threadIdx.x / CH, k = threadIdx.x % CH;
+		if (k < nch) {
+			zstate[((long) (c0 + k) * S + st) * 2] = carry[st][k].x;
+			zstate[((long) (c0 + k) * S + st) * 2 + 1] = carry[st][k].y;
+		}
 	}
+}
+
+template <int CH>
+static int bq_launch(const double *in, double *out, const double *tbl, double *zstate, int C, int S, long frames, cudaStream_t st)
+{
+	LAUNCH((k_bq_cascade<CH>), (C + CH - 1) / CH, BqCfg<CH>::THREADS, (size_t) CH * S * BQ_TBL * sizeof(double), st, in, out, tbl, zstate, C, S, frames);
+	return 0;
 }
 
 struct BiquadOp : Op {
@@ -157,8 +200,16 @@ struct BiquadOp : Op {
 	{
 		if (frames <= 0) return 0;
 		ProfScope prof("biquad", st);
-		LAUNCH(k_bq_cascade, channels, 32 * BQ_WARPS, (size_t) S * BQ_TBL * sizeof(double), st, in, out, d_tbl, d_zstate, channels, S, frames);
-		return frames;
+		// channels per CTA: wider rows per load as long as the grid still covers the SMs
+		static const int force = getenv("DSP_B200_BQ_CH") ? atoi(getenv("DSP_B200_BQ_CH")) : 0;
+		// Always channel pairs: the scan's association order depends on the chunks per warp, and a channel's
+		// result must not depend on how the chain was sharded (tests: sharded == unsharded, bit for bit).
+		const int chp = force ? force : 2;
+		int rc;
+		if (chp == 4) rc = bq_launch<4>(in, out, d_tbl, d_zstate, channels, S, frames, st);
+		else if (chp == 2) rc = bq_launch<2>(in, out, d_tbl, d_zstate, channels, S, frames, st);
+		else rc = bq_launch<1>(in, out, d_tbl, d_zstate, channels, S, frames, st);
+		return rc ? -1 : frames;
 	}
 };
 
@@ -186,8 +237,8 @@ Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 			// G[i] = A^(L-1-i) B, i = L-1 .. 0, and A^L on the way
 			long double g[2] = { Bv[0], Bv[1] };
 			for (int i = BQ_L - 1; i >= 0; --i) {
-				t[5 + 4 * BQ_NPOW + 2 * i] = (double) g[0];
-				t[5 + 4 * BQ_NPOW + 2 * i + 1] = (double) g[1];
+				t[BQ_OFF_G + 2 * i] = (double) g[0];
+				t[BQ_OFF_G + 2 * i + 1] = (double) g[1];
 				const long double n0 = A[0] * g[0] + A[1] * g[1], n1 = A[2] * g[0] + A[3] * g[1];
 				g[0] = n0; g[1] = n1;
 			}
@@ -198,7 +249,7 @@ Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 			}
 			// A^(L 2^r) by repeated squaring
 			for (int r = 0; r < BQ_NPOW; ++r) {
-				for (int k = 0; k < 4; ++k) t[5 + 4 * r + k] = (double) a[k];
+				for (int k = 0; k < 4; ++k) t[BQ_OFF_P + 4 * r + k] = (double) a[k];
 				const long double u[4] = { a[0] * a[0] + a[1] * a[2], a[0] * a[1] + a[1] * a[3], a[2] * a[0] + a[3] * a[2], a[2] * a[1] + a[3] * a[3] };
 				for (int k = 0; k < 4; ++k) a[k] = u[k];
 			}

@@ -248,6 +248,7 @@ struct L0Args {
 	double *carry;           // [s][N]
 	const double2 *tw, *ptw;
 	int n_ch;
+	const double2 *init;     // [s][N] spectrum added to S before the inverse transform (NULL: none)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p)
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 				prefetch_rows(fc_ + (long) sl * N, (long) N * sizeof(double2), t, T);
 			}
 			prefetch_rows(a.carry + (long) s * N, (long) N * sizeof(double), t, T);
+			if (a.init) prefetch_rows(a.init + (long) s * N, (long) N * sizeof(double2), t, T);
 		}
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 		double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride;
 		const double2 *H = a.H + (long) s * a.h_ch_stride;
 		double2 *X = fdl + (long) a.slot * N;
+		const double2 *init = a.init ? a.init + (long) s * N : nullptr;
 		double2 w[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) w[i] = __ldg(&a.tw[t + i * T]);
@@ -353,6 +356,13 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 				if (k == 0) { Sk.x = fma(xk.x, hk.x, Sk.x); Sk.y = fma(xk.y, hk.y, Sk.y); }
 				else Sk = cmac(Sk, xk, hk);
 				Sn = cmac(Sn, xn, hn);
+			}
+			if (init) {
+				// what the other partitions of this level contribute (MAC kernels, a block period ahead):
+				// summed here, in the frequency domain, so that the level needs one inverse transform
+				const double2 yk = init[k], yn = init[n];
+				Sk = cadd(Sk, yk);
+				Sn = cadd(Sn, yn);
 			}
 			if (k == 0) {
 				buf[0] = make_double2(0.5 * (Sk.x + Sk.y), -0.5 * (Sk.x - Sk.y));
@@ -698,14 +708,14 @@ struct FirLevel {
 	const double2 *tw = nullptr, *ptw = nullptr;
 	double2 *fdl = nullptr, *H = nullptr;
 	double *carry = nullptr, *pend = nullptr;
-	// last level only: partitions p >= 1 ("tail") run on a side stream one block period ahead
-	double *carry_tail = nullptr, *pend_tail[2] = { nullptr, nullptr };
+	// last level only: partitions p >= 1 ("tail") are summed by the MAC kernels on a side stream, one block
+	// period ahead, into a spectrum that the level's partition-0 kernel adds before its inverse transform
+	bool tail = false;
 	long blk = 0;                 // completed blocks of this level
 
 	void free_all()
 	{
 		dev_free(fdl); dev_free(H); dev_free(carry); dev_free(pend);
-		dev_free(carry_tail); dev_free(pend_tail[0]); dev_free(pend_tail[1]);
 	}
 };
 
@@ -729,17 +739,16 @@ struct FirOp : Op {
 	int *d_ch_map = nullptr;
 	double *d_hist = nullptr, *d_ytmp = nullptr, *d_pre = nullptr, *d_h0 = nullptr;
 	double2 *d_Y = nullptr;              // [n_sel][max B]
-	double2 *d_Y_side = nullptr;         // same, for the side stream
+	double2 *d_Y_side = nullptr;         // [n_sel][B last]: the tail spectrum of the next block period (side stream)
 	double *d_ring = nullptr, *d_ltmp = nullptr;
-	// side stream: the last level's tail (MAC over p >= 1 + inverse) overlaps the main stream's next period
+	// side stream: the upper levels' partition-0 kernels and the last level's tail MAC overlap the main stream
 	cudaStream_t side = nullptr;
-	cudaEvent_t ev_main = nullptr, ev_urgent = nullptr, ev_side[2] = { nullptr, nullptr };
+	cudaEvent_t ev_main = nullptr, ev_urgent = nullptr;
 	// time-batched tail (see k_fir_mac_batch): V spectra for 2 T block periods, produced T at a time on a second side stream
 	int t_batch = 0;
 	double2 *d_V = nullptr;
 	cudaStream_t side2 = nullptr;
 	cudaEvent_t ev_batch[2] = { nullptr, nullptr }, ev_main2 = nullptr;
-	long waited_period = -1;
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
 	long abs_pos = 0;                    // frames consumed so far (level-0 block = abs_pos / B0, offset = abs_pos % B0)
@@ -774,8 +783,6 @@ struct FirOp : Op {
 		dev_free(d_V);
 		if (ev_main) cudaEventDestroy(ev_main);
 		if (ev_urgent) cudaEventDestroy(ev_urgent);
-		for (cudaEvent_t e : ev_side)
-			if (e) cudaEventDestroy(e);
 		for (int l = 0; l < n_levels; ++l) lv[l].free_all();
 		dev_free(d_Y_side);
 		dev_free(d_ch_map); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
@@ -825,15 +832,11 @@ struct FirOp : Op {
 				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_urgent, cudaEventDisableTiming), return -1);
-				CUDA_TRY(cudaEventCreateWithFlags(&ev_side[0], cudaEventDisableTiming), return -1);
-				CUDA_TRY(cudaEventCreateWithFlags(&ev_side[1], cudaEventDisableTiming), return -1);
 			}
 			if (l > 0 && l == n_levels - 1 && L.P > 1) {
-				L.carry_tail = dev_alloc<double>((size_t) n_sel * L.B);
-				L.pend_tail[0] = dev_alloc<double>((size_t) n_sel * L.B);
-				L.pend_tail[1] = dev_alloc<double>((size_t) n_sel * L.B);
+				L.tail = true;
 				d_Y_side = dev_alloc<double2>((size_t) n_sel * L.B);
-				if (!L.carry_tail || !L.pend_tail[0] || !L.pend_tail[1] || !d_Y_side) return -1;
+				if (!d_Y_side) return -1;
 				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
 				if (L.P >= 2 * FIR_T_BATCH + 2 && !(nb && nb[0] == '1')) {
 					t_batch = FIR_T_BATCH;
@@ -891,7 +894,7 @@ struct FirOp : Op {
 
 	void reset(cudaStream_t st) override
 	{
-		abs_pos = 0; pre_valid = false; waited_period = -1; urgent_pending = false;
+		abs_pos = 0; pre_valid = false; urgent_pending = false;
 		if (!planned) return;
 		if (side) cudaStreamSynchronize(side);
 		if (side2) cudaStreamSynchronize(side2);
@@ -899,11 +902,6 @@ struct FirOp : Op {
 		for (int l = 0; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			L.blk = 0;
-			if (L.carry_tail) {
-				cudaMemsetAsync(L.carry_tail, 0, (size_t) n_sel * L.B * sizeof(double), st);
-				cudaMemsetAsync(L.pend_tail[0], 0, (size_t) n_sel * L.B * sizeof(double), st);
-				cudaMemsetAsync(L.pend_tail[1], 0, (size_t) n_sel * L.B * sizeof(double), st);
-			}
 			cudaMemsetAsync(L.fdl, 0, (size_t) n_sel * L.P * L.B * sizeof(double2), st);
 			cudaMemsetAsync(L.carry, 0, (size_t) n_sel * L.B * sizeof(double), st);
 			if (L.pend) cudaMemsetAsync(L.pend, 0, (size_t) n_sel * L.B * sizeof(double), st);
@@ -940,12 +938,13 @@ struct FirOp : Op {
 
 	// After level 0 finished a block: every larger level whose block just completed is advanced -- on the
 	// SIDE stream, so that the caller's stream (and, in host mode, the D2H of the block just produced and
-	// the H2D of the next one) is not held up by work whose result is only due later:
-	//   - partition 0 of the level is due in the very next block period: fused kernel (spectrum into the
-	//     level's FDL, result into `pend`), `ev_urgent` tells the main stream when it is there;
-	//   - the last level's partitions p >= 1 only involve blocks that were complete one period ago:
-	//     R_{q+1} = sum_{p>=1} X_{q+1-p} H_p is launched now (block q just completed) and consumed in
-	//     period q+2, so the HBM-streaming MAC has a whole period to overlap with the FFT kernels.
+	// the H2D of the next one) is not held up:
+	//   - the level's result for the block period that starts now is due at once: fused kernel (spectrum
+	//     into the level's FDL, S = X_q H_0 + Y_q, inverse, result into `pend`), `ev_urgent` tells the main
+	//     stream when it is there;
+	//   - Y_q = sum_{p>=1} X_{q-p} H_p (last level only) involves blocks that were complete one period
+	//     earlier: Y_{q+1} is launched right now and consumed by the fused kernel of the NEXT period, so the
+	//     HBM-streaming MAC has a whole period to overlap with the FFT kernels.
 	int advance_upper_levels(cudaStream_t st)
 	{
 		// Everything goes to the side stream: in host mode the D2H of this block and the H2D of the next are not
@@ -968,6 +967,7 @@ struct FirOp : Op {
 			f.H = L.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 			f.P = 1; f.slot = (int) (L.blk % L.P);
 			f.out = L.pend; f.out_ch_stride = L.B; f.carry = L.carry; f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
+			f.init = (L.tail && L.blk >= 1) ? d_Y_side : nullptr;   // Y of this block: launched one period ago, same stream
 			if (launch_level0(L.B, f, us)) return -1;
 			++L.blk;
 		}
@@ -975,10 +975,10 @@ struct FirOp : Op {
 		CUDA_TRY(cudaEventRecord(ev_urgent, us), return -1);
 		urgent_pending = (us != st);
 		FirLevel &L = lv[n_levels - 1];
-		if (L.carry_tail && abs_pos % L.B == 0) {
-			const long q1 = L.blk;   // R_{q+1}, q = the block that just completed
+		if (L.tail && abs_pos % L.B == 0) {
+			const long q1 = L.blk;   // Y_{q+1}, q = the block that just completed
 			if (t_batch > 0) {
-				// R_j = U_j + V_j, j = q1: U_j = sum_{1<=p<=T} X_{j-p} H_p now, V_j from the batch launched at
+				// Y_j = U_j + V_j, j = q1: U_j = sum_{1<=p<=T} X_{j-p} H_p now, V_j from the batch launched at
 				// the end of period T*floor((j-2)/T) (zero before the first batch: those blocks do not exist)
 				const int T = t_batch;
 				if (q1 >= 2) {
@@ -989,11 +989,6 @@ struct FirOp : Op {
 				mac(L, 1, T + 1, q1, ts, d_Y_side, init);
 			}
 			else mac(L, 1, L.P, q1, ts, d_Y_side);
-			InvArgs v = {};
-			v.Y = d_Y_side; v.out = L.pend_tail[q1 & 1]; v.out_ch_stride = L.B; v.carry = L.carry_tail;
-			v.flags = INV_OUT | INV_UPDATE_CARRY; v.tw = L.tw; v.ptw = L.ptw; v.n_ch = n_sel;
-			if (launch_inv(L.B, v, ts)) return -1;
-			CUDA_TRY(cudaEventRecord(ev_side[q1 & 1], ts), return -1);
 			const long q = q1 - 1;
 			if (t_batch > 0 && q % t_batch == 0) {
 				// X_q is in the FDL once the partition-0 kernel of this block has run (ev_urgent on the side stream)
@@ -1014,39 +1009,26 @@ struct FirOp : Op {
 		return 0;
 	}
 
-	// What the unstash / head kernels add on top of level 0 for the frames starting at `first_frame_abs`.
-	// In period q of the last level the tail result R_{q-1} is consumed (launched at the end of period
-	// q-2, see advance_upper_levels); side_wait() makes `st` wait for it, once per period, right before
-	// the first kernel that reads it.
+	// What the unstash / head kernels add on top of level 0 for the frames starting at `first_frame_abs`:
+	// every upper level's result for its current block period.
 	PendArgs pend_args(long first_frame_abs) const
 	{
 		PendArgs p = {};
 		for (int l = 1; l < n_levels; ++l) {
 			const FirLevel &L = lv[l];
-			const int off = (int) (first_frame_abs % L.B);
-			p.buf[p.n] = L.pend; p.len[p.n] = L.B; p.off[p.n] = off;
+			p.buf[p.n] = L.pend; p.len[p.n] = L.B; p.off[p.n] = (int) (first_frame_abs % L.B);
 			++p.n;
-			if (L.carry_tail) {
-				const long q = first_frame_abs / L.B;
-				p.buf[p.n] = L.pend_tail[(q + 1) & 1]; p.len[p.n] = L.B; p.off[p.n] = off;   // (q - 1) & 1
-				++p.n;
-			}
 		}
 		return p;
 	}
 
-	void side_wait(long first_frame_abs, cudaStream_t st)
+	// the main stream waits for the upper levels' kernels right before the first kernel that reads `pend`
+	void side_wait(long, cudaStream_t st)
 	{
 		if (urgent_pending) {
 			cudaStreamWaitEvent(st, ev_urgent, 0);
 			urgent_pending = false;
 		}
-		const FirLevel &L = lv[n_levels - 1];
-		if (!L.carry_tail) return;
-		const long q = first_frame_abs / L.B;
-		if (q == waited_period) return;
-		if (q >= 2) cudaStreamWaitEvent(st, ev_side[(q + 1) & 1], 0);
-		waited_period = q;
 	}
 
 	int ensure_pre(cudaStream_t st)

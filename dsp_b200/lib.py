@@ -48,6 +48,8 @@ SIGNATURES = {
     "dspb200_chain_drain_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p]),
     "dspb200_chain_reset": (None, [C.c_void_p]),
     "dspb200_chain_sync": (C.c_int, [C.c_void_p]),
+    "dspb200_chain_submit_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "dspb200_chain_wait": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "dspb200_biquad_design": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _dp]),
     "dspb200_hilbert_taps": (C.c_int, [C.c_long, C.c_double, _dp]),
     "dspb200_resample_params": (C.c_int, [C.c_int, C.c_int, C.c_double, _lp]),
@@ -226,6 +228,15 @@ class Chain:
 
     def run_raw(self, frames, in_ptr, out_ptr):
         return _check(lib().dspb200_chain_run_host(self.h, int(frames), in_ptr, out_ptr), "run_host")
+
+    def submit_raw(self, frames, in_ptr, out_ptr):
+        """run_raw without the wait: returns (out_frames, ticket); buffers stay busy until wait(ticket)."""
+        t = C.c_ulonglong(0)
+        n = _check(lib().dspb200_chain_submit_host(self.h, int(frames), in_ptr, out_ptr, C.byref(t)), "submit_host")
+        return n, t.value
+
+    def wait(self, ticket):
+        _check(lib().dspb200_chain_wait(self.h, int(ticket)), "wait")
 
     def run_device(self, shard, frames, d_in, d_out, stream=None):
         """Mode D: raw device pointers (ints), asynchronous on `stream` (cudaStream_t as int)."""

@@ -105,6 +105,15 @@ long dspb200_chain_max_out_frames(const dspb200_chain *c, long in_frames);
 /* Mode A: host buffers, synchronous; in/out hold frames*channels (out: max_out_frames*channels)
  * doubles; in == out allowed.  Returns output frames. */
 long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, double *out);
+/* The same work without the final wait (throughput frontends: file -> file, offline rendering).
+ * Enqueues copy-in, the operators and copy-out of this block on the shards' streams and returns the
+ * frame count `out` will hold; `in` and `out` must stay valid and untouched until
+ * dspb200_chain_wait(chain, *ticket) (or dspb200_chain_sync) returns.  Blocks submitted back to back
+ * overlap: copy-in of block k+1, kernels of block k and copy-out of block k-1 run concurrently
+ * (use page-locked buffers, dspb200_host_alloc).  At most 8 tickets may be outstanding.
+ * dspb200_chain_run_host == submit + wait; the two may be mixed freely. */
+long dspb200_chain_submit_host(dspb200_chain *c, long frames, const double *in, double *out, unsigned long long *ticket);
+int  dspb200_chain_wait(dspb200_chain *c, unsigned long long ticket);
 
 /* Mode D: one shard, device-resident interleaved buffers of that shard's channel count,
  * enqueued on `stream` (a cudaStream_t; NULL = the legacy default stream), asynchronous.
