@@ -16,7 +16,7 @@
 // and the emitted stream is y[out_delay + q].  The n x in_len tap table G (0.75 MB for
 // 44100->48000) is built on the device at init from the reference's own sinc samples; the hot
 // kernel is a per-channel dot product with lanes along channels, so every load of the
-// interleaved input is a coalesced row and the tap is a warp-uniform (broadcast) load.
+// interleaved input is a coalesced row and the taps are broadcast loads from shared memory.
 // The reference's per-call frame pacing is replayed by an integer state machine on the host,
 // so each call emits exactly the frame count resample_effect_run() would.
 #include "common.cuh"
@@ -130,68 +130,125 @@ __global__ void k_rs_table(const double2 *S, int K, int n, int in_len, double *G
 }
 
 // out[q][c] = sum_t G[(m d) % n][t] * x[(m d) / n - t][c],  m = m0 + q;  x lives in a ring of rows.
-// Register-blocked: a warp produces R consecutive output frames for 32*CH channels (lane = CH adjacent
-// channels).  It walks the input rows i downwards once; every row is loaded once (CH doubles per lane,
-// coalesced) and feeds all R outputs, each with its own tap G[ph_r][i_hi_r - i] (warp-uniform load).
-// Tap rows are zero-padded by `pad` on both sides, so the ragged ends of the R tap windows need no
-// branches.  2 R CH flops per (1 + R) loads.
-template <int R, int CH>
-__global__ void __launch_bounds__(128) k_rs_poly(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
-                                                 int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
+// A CTA produces Q = R*WARPS consecutive output frames for 32*CH channels: warp w owns frames R w .. R w + R-1,
+// lane = CH adjacent channels, R x CH accumulators in registers.  The Q tap windows are first gathered into
+// shared memory as S[k][r] = G[ph_r][ih_r - (i_top - k)] -- row k holds the taps the Q outputs apply to
+// input row i_top - k (zero where a window has not begun or has ended: the rows of G are zero-padded by
+// `pad` on both sides, and S is zero past the end of the span, so the loop needs no bounds) -- in chunks of
+// ROWS rows.  The warps then walk the input rows downwards once, one software-pipeline stage (RS_G rows)
+// ahead of the arithmetic: every row is loaded once per warp (CH doubles per lane, coalesced; the warps of
+// the CTA read the same rows within a few iterations of each other, so all but one of the loads hit in L1)
+// and meets its R taps as R/2 broadcast 128-bit shared loads.
+// The kernel is bound by the L1/LSU data pipe before it is bound by FP64 issue (ncu: l1tex data-pipe 79 %
+// busy at 47 % FP64 with an 8 x 4 register tile; a broadcast LDS.128 costs 2 wavefronts, a coalesced
+// LDG.128 about 10), so the register tile is as large as the register file allows: 16 outputs x 4
+// channels = 64 accumulators per lane, 2 LDG.128 + 8 LDS.128 per 64 DFMA.
+// History: (1) taps by warp-uniform global loads: the 160 phases' rows -- 0.75 MB for 44100->48000 -- do not
+// fit in L1, the kernel sat on L2 latency at 31 % of the FP64 rate; (2) taps in shared memory, 8 x 4 tile:
+// 45-49 %, LSU-bound as above.
+constexpr int RS_G = 4;          // input rows per software-pipeline stage
+constexpr int RS_QMAX = 64;      // most output frames per CTA of any variant (sizes the zero padding of G's rows)
+
+template <int R, int CH, int WARPS>
+struct RsCfg {
+	static constexpr int Q = R * WARPS;             // output frames per CTA
+	static constexpr int LD = Q + 2;                // row stride of S in doubles: 16-byte aligned rows, column stores spread over banks
+	static constexpr int ROWS = (4096 / Q) & ~(RS_G - 1);   // input rows per chunk (about 32 KB of taps)
+	static constexpr int THREADS = 32 * WARPS;
+	static_assert(Q <= RS_QMAX && ROWS % RS_G == 0 && ROWS % 32 == 0, "tile shape");
+};
+
+// One pipeline stage of input rows.  No bounds: the ring is zero-initialised and only ever walked
+// backwards, rows outside a tile's span meet zero taps.
+template <int CH>
+__device__ __forceinline__ void rs_load_rows(double (&x)[RS_G][CH], const double *col, long &row, long ring_len, int C)
 {
+#pragma unroll
+	for (int j = 0; j < RS_G; ++j) {
+		const double *p = col + row * C;
+		if (CH == 4) {
+			const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+			x[j][0] = a.x; x[j][1 % CH] = a.y; x[j][2 % CH] = b.x; x[j][3 % CH] = b.y;
+		}
+		else if (CH == 2) {
+			const double2 a = *reinterpret_cast<const double2 *>(p);
+			x[j][0] = a.x; x[j][1 % CH] = a.y;
+		}
+		else x[j][0] = p[0];
+		row = (row == 0) ? ring_len - 1 : row - 1;
+	}
+}
+
+template <int R, int CH, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_rs_poly(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
+                                                              int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
+{
+	using Cfg = RsCfg<R, CH, WARPS>;
+	constexpr int Q = Cfg::Q, LD = Cfg::LD, ROWS = Cfg::ROWS;
+	__shared__ __align__(16) double S[ROWS * LD];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int c0 = (blockIdx.y * 32 + lane) * CH;
-	const long q0 = ((long) blockIdx.x * 4 + warp) * R;
-	if (q0 >= n_out) return;
-	long ih[R];
-	const double *g[R];
-#pragma unroll
-	for (int r = 0; r < R; ++r) {
-		long q = q0 + r;
-		if (q >= n_out) q = n_out - 1;   // duplicates the last frame's work; not stored
-		const long md = (m0 + q) * d;
-		ih[r] = md / n;
-		g[r] = G + (md - ih[r] * n) * g_stride + pad;
-	}
-	const long i_top = ih[R - 1];
-	long i_bot = ih[0] - in_len + 1;
+	const long q0 = (long) blockIdx.x * Q;
+	// first and last output of the tile fix the span of input rows (q clamped: a partial last tile repeats
+	// the last frame's work and does not store it)
+	const long q_last = (q0 + Q - 1 < n_out) ? q0 + Q - 1 : n_out - 1;
+	const long i_top = ((m0 + q_last) * d) / n;
+	long i_bot = ((m0 + q0) * d) / n - in_len + 1;
 	if (i_bot < 0) i_bot = 0;   // rows before the stream start are zero
-#pragma unroll
-	for (int r = 0; r < R; ++r) g[r] += ih[r] - i_top;   // tap index of row i_top (<= 0, inside the left pad)
+	const int k_end = (int) (i_top - i_bot + 1);
 	double acc[R][CH];
 #pragma unroll
 	for (int r = 0; r < R; ++r)
 #pragma unroll
 		for (int h = 0; h < CH; ++h) acc[r][h] = 0.0;
 	const bool act = c0 < C;
-	long row = i_top % ring_len;
-	const double *col = ring + (act ? c0 : 0);
-	for (long i = i_top; i >= i_bot; --i) {
-		double x[CH];
-		const double *p = col + row * C;
-		if (CH == 4) {
-			const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
-			x[0] = a.x; x[1] = a.y; x[2 % CH] = b.x; x[3 % CH] = b.y;
-		}
-		else if (CH == 2) {
-			const double2 a = *reinterpret_cast<const double2 *>(p);
-			x[0] = a.x; x[1 % CH] = a.y;
-		}
-		else x[0] = p[0];
+	const double *col = ring + (act ? c0 : 0);   // lanes past the last channel compute on channel 0 and do not store
+	long row = i_top % ring_len;   // next row to LOAD (runs one stage ahead of the multiplication)
+
+	double xn[RS_G][CH];
+	rs_load_rows<CH>(xn, col, row, ring_len, C);
+	for (int kk = 0; kk < k_end; kk += ROWS) {
+		// taps of the next ROWS rows: warp w gathers columns w, w + WARPS, ...; a lane reads consecutive taps of
+		// one row of G (coalesced) and stores them down a column of S
+		if (kk > 0) __syncthreads();
+		for (int fr = warp; fr < Q; fr += WARPS) {
+			long q = q0 + fr;
+			if (q >= n_out) q = n_out - 1;
+			const long md = (m0 + q) * d, ih = md / n;
+			const double *gsrc = G + (md - ih * n) * g_stride + pad + (ih - i_top) + kk;   // tap for row i_top - kk
 #pragma unroll
-		for (int r = 0; r < R; ++r) {
-			const double w = __ldg(g[r]);
-			++g[r];
-#pragma unroll
-			for (int h = 0; h < CH; ++h) acc[r][h] = fma(w, x[h], acc[r][h]);
+			for (int k = lane; k < ROWS; k += 32) S[k * LD + fr] = (kk + k < k_end) ? __ldg(gsrc + k) : 0.0;
 		}
-		row = (row == 0) ? ring_len - 1 : row - 1;
+		__syncthreads();
+		const int stages = (k_end - kk < ROWS) ? (k_end - kk + RS_G - 1) / RS_G : ROWS / RS_G;
+		for (int sg = 0; sg < stages; ++sg) {
+			double x[RS_G][CH];
+#pragma unroll
+			for (int j = 0; j < RS_G; ++j)
+#pragma unroll
+				for (int h = 0; h < CH; ++h) x[j][h] = xn[j][h];
+			rs_load_rows<CH>(xn, col, row, ring_len, C);
+#pragma unroll
+			for (int j = 0; j < RS_G; ++j) {
+				const double2 *w2 = reinterpret_cast<const double2 *>(&S[(sg * RS_G + j) * LD + warp * R]);
+#pragma unroll
+				for (int r = 0; r < R; r += 2) {
+					const double2 w = w2[r / 2];
+#pragma unroll
+					for (int h = 0; h < CH; ++h) {
+						acc[r][h] = fma(w.x, x[j][h], acc[r][h]);
+						acc[r + 1][h] = fma(w.y, x[j][h], acc[r + 1][h]);
+					}
+				}
+			}
+		}
 	}
 	if (!act) return;
 #pragma unroll
 	for (int r = 0; r < R; ++r) {
-		if (q0 + r >= n_out) break;
-		double *o = out + (q0 + r) * C + c0;
+		const long q = q0 + warp * R + r;
+		if (q >= n_out) break;
+		double *o = out + q * C + c0;
 		if (CH == 4) {
 			*reinterpret_cast<double2 *>(o) = make_double2(acc[r][0], acc[r][1 % CH]);
 			*reinterpret_cast<double2 *>(o + 2) = make_double2(acc[r][2 % CH], acc[r][3 % CH]);
@@ -201,7 +258,127 @@ __global__ void __launch_bounds__(128) k_rs_poly(const double *__restrict__ ring
 	}
 }
 
-constexpr int RS_R = 8;   // output frames per warp
+// ---- the same sum on the FP64 tensor cores --------------------------------------------------------
+// Y[q][c] = sum_k S[k][q] X[k][c] is a GEMM (M = output frames, N = channels, K = input rows) whose A operand
+// is the tap tile above and whose B operand is the input ring itself.  mma.sync m8n8k4 f64 (DMMA) issues at
+// the DFMA rate on this part (scripts/micro/dmma_probe.cu: 37.1 against 34.1 TFLOP/s) but takes its
+// operands as fragments -- one A and one B double per lane feed 256 FMAs -- so the L1/LSU traffic per flop
+// drops by about 4x against the register-tiled FMA loop, which is what bounded that loop.
+//   warp tile: 32 outputs (MT = 4 m-tiles) x 32 channels (NT = 4 n-tiles), 32 accumulator doubles per lane;
+//   CTA: WARPS warps side by side along the channels, all on the same 32 outputs (one tap tile per CTA, the
+//   input rows are read exactly once per CTA);
+//   A fragment (m = lane/4, k = lane%4) = S[k0 + lane%4][8 mt + lane/4]: row stride 40 doubles puts the four
+//   rows of a fragment on two disjoint halves of the banks (2 wavefronts for 256 bytes);
+//   B fragment (k = lane%4, n = lane/4): n-tile j, column n is channel c0 + 4 n + j, so a lane's four
+//   fragments are 4 adjacent channels of ONE input row -- two 128-bit loads, a warp load instruction covers
+//   4 rows x 256 contiguous bytes -- and a lane's 8 results per output frame are 8 adjacent channels.
+// Needs channels % 4 == 0 (16-byte aligned rows); other shapes use the FMA kernel above.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+{
+	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+constexpr int RSM_Q = 32, RSM_LD = 40, RSM_ROWS = 128;
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_rs_mma(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
+                                                       int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
+{
+	constexpr int MT = 4, NT = 4, Q = RSM_Q, LD = RSM_LD, ROWS = RSM_ROWS;
+	__shared__ __align__(16) double S[ROWS * LD];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int g = lane >> 2, t = lane & 3;
+	const int c0w = (blockIdx.y * WARPS + warp) * 32;
+	const long q0 = (long) blockIdx.x * Q;
+	const long q_last = (q0 + Q - 1 < n_out) ? q0 + Q - 1 : n_out - 1;
+	const long i_top = ((m0 + q_last) * d) / n;
+	long i_bot = ((m0 + q0) * d) / n - in_len + 1;
+	if (i_bot < 0) i_bot = 0;   // rows before the stream start are zero
+	const int k_end = (int) (i_top - i_bot + 1);
+	// gather pointers: this lane fills columns g, g + 8, g + 16, g + 24 of S (rows k = 4 kg + t)
+	const double *gs[MT];
+#pragma unroll
+	for (int m = 0; m < MT; ++m) {
+		long q = q0 + g + 8 * m;
+		if (q >= n_out) q = n_out - 1;
+		const long md = (m0 + q) * d, ih = md / n;
+		gs[m] = G + (md - ih * n) * g_stride + pad + (ih - i_top);   // tap of row i_top (index <= 0: inside the left pad)
+	}
+	double acc[MT][NT][2];
+#pragma unroll
+	for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+		for (int j = 0; j < NT; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+	// B operand: 4 adjacent channels of row i_top - (4 step + t); lanes past the last channel read channel 0
+	const int cl = c0w + 4 * g;
+	const double *col = ring + ((cl < C) ? cl : 0);
+	long row = (i_top - t) % ring_len;
+	if (row < 0) row += ring_len;
+	double bn[NT];
+	{
+		const double *p = col + row * C;
+		const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+		bn[0] = u.x; bn[1] = u.y; bn[2] = v.x; bn[3] = v.y;
+		row -= 4;
+		if (row < 0) row += ring_len;
+	}
+	for (int kk = 0; kk < k_end; kk += ROWS) {
+		if (kk > 0) __syncthreads();
+		for (int kg = warp; kg < ROWS / 4; kg += WARPS) {
+			const int k = 4 * kg + t;
+			const bool in = kk + k < k_end;
+#pragma unroll
+			for (int m = 0; m < MT; ++m) S[k * LD + g + 8 * m] = in ? __ldg(gs[m] + kk + k) : 0.0;
+		}
+		__syncthreads();
+		const int left = k_end - kk;
+		const int steps = (left < ROWS) ? (left + 3) / 4 : ROWS / 4;
+		for (int st = 0; st < steps; ++st) {
+			double b[NT];
+#pragma unroll
+			for (int j = 0; j < NT; ++j) b[j] = bn[j];
+			{
+				const double *p = col + row * C;
+				const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+				bn[0] = u.x; bn[1] = u.y; bn[2] = v.x; bn[3] = v.y;
+				row -= 4;
+				if (row < 0) row += ring_len;
+			}
+			double a[MT];
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt) a[mt] = S[(4 * st + t) * LD + 8 * mt + g];
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+				for (int j = 0; j < NT; ++j) dmma884(acc[mt][j], a[mt], b[j]);
+		}
+	}
+	// D fragment: row lane/4, columns 2 t and 2 t + 1 of n-tile j = channels c0w + 8 t + j and c0w + 8 t + 4 + j
+	const int ch = c0w + 8 * t;
+#pragma unroll
+	for (int mt = 0; mt < MT; ++mt) {
+		const long q = q0 + 8 * mt + g;
+		if (q >= n_out) continue;
+		double *o = out + q * C + ch;
+		if (ch < C) {
+			*reinterpret_cast<double2 *>(o) = make_double2(acc[mt][0][0], acc[mt][1][0]);
+			*reinterpret_cast<double2 *>(o + 2) = make_double2(acc[mt][2][0], acc[mt][3][0]);
+		}
+		if (ch + 4 < C) {
+			*reinterpret_cast<double2 *>(o + 4) = make_double2(acc[mt][0][1], acc[mt][1][1]);
+			*reinterpret_cast<double2 *>(o + 6) = make_double2(acc[mt][2][1], acc[mt][3][1]);
+		}
+	}
+}
+
+template <int R, int CH, int WARPS, int MINB>
+static void rs_launch(cudaStream_t st, const double *ring, long ring_len, int C, const double *G, int g_stride, int pad,
+                      const ResampleParams &p, long m0, long n_out, double *out)
+{
+	using Cfg = RsCfg<R, CH, WARPS>;
+	const dim3 grid((unsigned) ceil_div(n_out, Cfg::Q), (unsigned) ceil_div(C, 32 * CH));
+	LAUNCH((k_rs_poly<R, CH, WARPS, MINB>), grid, Cfg::THREADS, 0, st, ring, ring_len, C, G, g_stride, pad, p.n, p.d, p.in_len, m0, n_out, out);
+}
 
 // move the live rows of the input ring into a bigger ring (absolute frame a lives at a % len)
 __global__ void k_rs_ring_grow(const double *old_ring, long old_len, double *new_ring, long new_len, int C, long a0, long rows)
@@ -307,23 +484,22 @@ struct ResampleOp : Op {
 		const long first_m = emit_pos;   // emission is one contiguous raw range per call
 		if (oframes > 0) {
 			ProfScope prof("resample", st);
-			// pick the register tile so that the grid still fills the chip: wide tiles (8 frames x 4 channels
-			// per lane) have the best flop/load ratio, narrow ones more warps
-			const long warps84 = (long) ceil_div(oframes, 8) * ceil_div(C, 128);
-			const long warps82 = (long) ceil_div(oframes, 8) * ceil_div(C, 64);
-			const long want = 148L * 24;
-			if (C % 4 == 0 && warps84 >= want) {
-				LAUNCH((k_rs_poly<8, 4>), dim3(ceil_div(oframes, 32), ceil_div(C, 128)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+			// DSP_B200_RS_TILE: 0 auto, 1..3 the FMA tiles (16x4, 16x2, 8x1), 4 tensor-core kernel
+			static const int force = getenv("DSP_B200_RS_TILE") ? atoi(getenv("DSP_B200_RS_TILE")) : 0;
+			int tile = (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 3;
+			if (force >= 1 && force <= 4 && !(((force == 1 || force == 4) && C % 4) || (force == 2 && C % 2))) tile = force;
+			if (tile == 4) {
+				// 4 warps (128 channels) per CTA when that still gives every SM a few CTAs, else 2 or 1
+				const long tiles = ceil_div(oframes, RSM_Q);
+				const int w = (C >= 128 && tiles * ceil_div(C, 128) >= 148L * 3) ? 4 : (C >= 64 && tiles * ceil_div(C, 64) >= 148L * 2) ? 2 : 1;
+				const dim3 grid((unsigned) tiles, (unsigned) ceil_div(C, 32 * w));
+				if (w == 4) LAUNCH((k_rs_mma<4>), grid, 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+				else if (w == 2) LAUNCH((k_rs_mma<2>), grid, 64, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+				else LAUNCH((k_rs_mma<1>), grid, 32, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
 			}
-			else if (C % 2 == 0 && warps82 >= want) {
-				LAUNCH((k_rs_poly<8, 2>), dim3(ceil_div(oframes, 32), ceil_div(C, 64)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
-			}
-			else if (C % 2 == 0) {
-				LAUNCH((k_rs_poly<4, 2>), dim3(ceil_div(oframes, 16), ceil_div(C, 64)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
-			}
-			else {
-				LAUNCH((k_rs_poly<4, 1>), dim3(ceil_div(oframes, 16), ceil_div(C, 32)), 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
-			}
+			else if (tile == 1) rs_launch<16, 4, 4, 2>(st, d_ring, ring_len, C, d_G, g_stride, g_pad, p, first_m, oframes, out);
+			else if (tile == 2) rs_launch<16, 2, 2, 6>(st, d_ring, ring_len, C, d_G, g_stride, g_pad, p, first_m, oframes, out);
+			else rs_launch<8, 1, 4, 4>(st, d_ring, ring_len, C, d_G, g_stride, g_pad, p, first_m, oframes, out);
 			emit_pos += oframes;
 		}
 		return oframes;
@@ -370,8 +546,8 @@ Op *make_resample_op(int slab_channels, int fs_in, int fs_out, double bandwidth,
 	}
 	double *d_sinc = dev_alloc<double>(sinc.size(), false);
 	double2 *d_S = dev_alloc<double2>((size_t) p.sinc_len + 1, false);
-	// R consecutive outputs span at most (R-1) d/n + 1 input rows more than one output does
-	op->g_pad = (int) (((long) (RS_R - 1) * p.d) / p.n + 2);
+	// Q consecutive outputs span at most (Q-1) d/n + 1 input rows more than one output does
+	op->g_pad = (int) (((long) (RS_QMAX - 1) * p.d) / p.n + 2);
 	op->g_stride = p.in_len + 2 * op->g_pad;
 	op->d_G = dev_alloc<double>((size_t) p.n * op->g_stride, true);
 	if (!d_sinc || !d_S || !op->d_G) return nullptr;
