@@ -281,7 +281,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 constexpr int RSM_Q = 32, RSM_LD = 40, RSM_ROWS = 128;
 
 template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) k_rs_mma(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
+__global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
                                                        int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
 {
 	constexpr int MT = 4, NT = 4, Q = RSM_Q, LD = RSM_LD, ROWS = RSM_ROWS;
@@ -295,15 +295,6 @@ __global__ void __launch_bounds__(32 * WARPS) k_rs_mma(const double *__restrict_
 	long i_bot = ((m0 + q0) * d) / n - in_len + 1;
 	if (i_bot < 0) i_bot = 0;   // rows before the stream start are zero
 	const int k_end = (int) (i_top - i_bot + 1);
-	// gather pointers: this lane fills columns g, g + 8, g + 16, g + 24 of S (rows k = 4 kg + t)
-	const double *gs[MT];
-#pragma unroll
-	for (int m = 0; m < MT; ++m) {
-		long q = q0 + g + 8 * m;
-		if (q >= n_out) q = n_out - 1;
-		const long md = (m0 + q) * d, ih = md / n;
-		gs[m] = G + (md - ih * n) * g_stride + pad + (ih - i_top);   // tap of row i_top (index <= 0: inside the left pad)
-	}
 	double acc[MT][NT][2];
 #pragma unroll
 	for (int mt = 0; mt < MT; ++mt)
@@ -324,11 +315,23 @@ __global__ void __launch_bounds__(32 * WARPS) k_rs_mma(const double *__restrict_
 	}
 	for (int kk = 0; kk < k_end; kk += ROWS) {
 		if (kk > 0) __syncthreads();
-		for (int kg = warp; kg < ROWS / 4; kg += WARPS) {
-			const int k = 4 * kg + t;
-			const bool in = kk + k < k_end;
+		{
+			// gather: this lane fills columns g, g + 8, g + 16, g + 24 of S, rows k = 4 kg + t (the pointers are
+			// rebuilt per chunk rather than kept in registers through the multiply loop)
+			const double *gs[MT];
 #pragma unroll
-			for (int m = 0; m < MT; ++m) S[k * LD + g + 8 * m] = in ? __ldg(gs[m] + kk + k) : 0.0;
+			for (int m = 0; m < MT; ++m) {
+				long q = q0 + g + 8 * m;
+				if (q >= n_out) q = n_out - 1;
+				const long md = (m0 + q) * d, ih = md / n;
+				gs[m] = G + (md - ih * n) * g_stride + pad + (ih - i_top) + kk;   // tap of row i_top - kk (index may be <= 0: left pad)
+			}
+			for (int kg = warp; kg < ROWS / 4; kg += WARPS) {
+				const int k = 4 * kg + t;
+				const bool in = kk + k < k_end;
+#pragma unroll
+				for (int m = 0; m < MT; ++m) S[k * LD + g + 8 * m] = in ? __ldg(gs[m] + k) : 0.0;
+			}
 		}
 		__syncthreads();
 		const int left = k_end - kk;
