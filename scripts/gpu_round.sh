@@ -15,5 +15,12 @@ if [ "$mode" = "full" ]; then
       python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fir_mac -s 10 -c 2 -o gpurun_out/prof_fir_mac -f \
       python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fir_level0 -s 12 -c 3 -o gpurun_out/prof_level0 -f \
+      python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_level0.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_bq_cascade -s 3 -c 1 -o gpurun_out/prof_bq -f \
+      python scripts/run_biquad.py > gpurun_out/ncu_bq.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_rs_mma -s 3 -c 1 -o gpurun_out/prof_rs -f \
+      python scripts/run_resample.py 1024 > gpurun_out/ncu_rs.log 2>&1
+  timeout 300 python scripts/bench_kernels.py > gpurun_out/kernels.json 2> gpurun_out/kernels.err
   ls -la gpurun_out
 fi
