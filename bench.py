@@ -195,6 +195,16 @@ def main():
     ap.add_argument("--e2e-slabs", type=int, default=4)
     a = ap.parse_args()
 
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) is sent to stderr, the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,7 +219,7 @@ def main():
             return 0
         r = cpu_reference_run(a.block, warm, steps=steps)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdspref.so not built (needs /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libdspref.so not built (needs /root/reference at build time)"})
             return 0
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
                 "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -217,7 +227,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -415,7 +425,7 @@ def main():
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum}
-        print(json.dumps(line))
+        emit(line)
     job.close()
     return 0
 
