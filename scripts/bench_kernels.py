@@ -81,4 +81,16 @@ d_out = torch.empty((F, C), dtype=torch.float64, device="cuda")
 ms, prof = timed(ch, blocks, d_out, F, steps=200, names=("fir_mac",))
 out["H_shared_ir"] = {"ms_per_block": ms, "Msamples_per_s": C * F / (ms * 1e-3) / 1e6, "fir_mac_us": prof["fir_mac"][0] / max(prof["fir_mac"][1], 1) * 1e3}
 ch.close()
+
+# C3: fir_p 131072 taps, 64 ch, per-channel IR; and the headline shape at the CLI's default block (2048) and a large one (65536)
+for tag, C, F, steps in (("C3_fir_p_64ch_block4096", 64, 4096, 200), ("H_block2048", 256, 2048, 300), ("H_block65536", 256, 65536, 12)):
+    ch = dsp_b200.Chain(48000, C).add_fir(bench.make_irs(131072, C), block_hint=F)
+    nb = 8 if F <= 4096 else 2
+    blocks = [torch.from_numpy(bench.make_block(F, C, i)).cuda() for i in range(nb)]
+    d_out = torch.empty((F, C), dtype=torch.float64, device="cuda")
+    ms, prof = timed(ch, blocks, d_out, F, steps=steps, warm=3, names=("fir_mac",))
+    out[tag] = {"ms_per_block": ms, "Msamples_per_s": C * F / (ms * 1e-3) / 1e6, "plan": ch.describe()}
+    ch.close()
+    del blocks, d_out
+    torch.cuda.empty_cache()
 print(json.dumps(out, indent=1))

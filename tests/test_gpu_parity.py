@@ -123,6 +123,34 @@ def test_resample_ratios(gpu_lib, have_ref, rates):
     ch.close()
 
 
+@pytest.mark.parametrize("channels", [1, 2, 4, 6, 36, 132])
+def test_resample_channel_counts_pick_every_kernel_variant(gpu_lib, have_ref, channels):
+    """channels % 4 == 0 runs on the FP64 tensor cores (k_rs_mma: 4, 36 = a partly filled warp, 132 = a
+    partly filled second CTA column), everything else on the FMA kernel (k_rs_poly: pairs for even counts,
+    single channels for odd ones); ragged call sizes on top."""
+    from oracle import restate
+    fi, fo = 44100, 48000
+    rng = np.random.default_rng(channels)
+    x = rng.standard_normal((5000, channels)) * 0.3
+    sizes = [1024, 7, 2048, 1, 900, 1020]
+    if have_ref:
+        from oracle import ref
+        r = ref.RefChain("resample %d" % fo, fi, channels)
+    else:
+        r = restate.Resampler(fi, fo, channels)
+    ch = gpu_lib.Chain(fi, channels).add_resample(fo)
+    pos = 0
+    for n in sizes:
+        blk = x[pos:pos + n]
+        pos += n
+        want = r.run(blk)
+        got = ch.run(blk).copy()
+        assert got.shape == want.shape
+        if want.size:
+            assert rms(got - want) <= RMS_TOL
+    ch.close()
+
+
 def test_full_size_impulse_response_property(gpu_lib):
     """Headline shape (256 ch x 131072 taps, per-channel IR, 4096-frame blocks): a delta in gives the
     IR back -- a size-independent known answer."""
