@@ -106,6 +106,10 @@ struct FwdArgs {
 	int slot;               // row within the channel
 	const double2 *tw, *ptw;   // split twiddles W_2N^k, per-pass butterfly twiddles
 	int n_ch;
+	// bulk form (gridDim.y > 1): block i = blockIdx.y reads the ring at (ring_off + i N) % ring_len and
+	// writes row (slot + i) % slot_rows; ring_len == 0: plain form
+	long ring_len, ring_off;
+	int slot_rows;
 };
 
 template <int N>
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_fwd(FwdArgs a)
 
 	if (active) {
 		const double *xs = a.in + (long) s * a.ch_stride;
+		if (a.ring_len > 0) xs += (a.ring_off + (long) blockIdx.y * N) % a.ring_len;
 		const bool aligned = ((reinterpret_cast<size_t>(xs) & 15) == 0);
 		const double2 *x = reinterpret_cast<const double2 *>(xs);
 		for (int n = t; n < N / 2; n += T) {
@@ -133,7 +138,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_fwd(FwdArgs a)
 	__syncthreads();
 	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
-		double2 *X = a.spec + (long) s * a.spec_ch_stride + (long) a.slot * N;
+		const int slot = (a.ring_len > 0) ? (a.slot + (int) blockIdx.y) % a.slot_rows : a.slot;
+		double2 *X = a.spec + (long) s * a.spec_ch_stride + (long) slot * N;
 		// every thread owns the 8 bin pairs (k, N-k), k = t + i T; thread 0 also owns k = 0 and k = N/2
 		double2 w[8];
 #pragma unroll
@@ -158,7 +164,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_fwd(FwdArgs a)
 	}
 }
 
-enum { INV_OUT = 1, INV_UPDATE_CARRY = 2 };
+enum { INV_OUT = 1, INV_UPDATE_CARRY = 2, INV_RAW = 4 };
+// INV_RAW (bulk form, block i = blockIdx.y): Y, out and carry are [i][s][N]-strided arrays; out gets the first
+// half of the inverse transform and carry the second half, nothing is added (k_fir_unstash_bulk overlaps them)
 
 struct InvArgs {
 	const double2 *Y;       // [s][N] packed spectra
@@ -180,8 +188,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 	const bool active = s < a.n_ch;
 	double2 *buf = smem + (size_t) g * FftCfg<N>::STRIDE;
 
+	const long boff = (a.flags & INV_RAW) ? (long) blockIdx.y * a.n_ch : 0;   // bulk form: rows of block i
 	if (active) {
-		const double2 *Y = a.Y + (long) s * N;
+		const double2 *Y = a.Y + (boff + s) * N;
 		double2 yk[8], yn[8], w[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
@@ -212,9 +221,19 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_inv(InvArgs a)
 	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
 		const double scale = 1.0 / N;
-		double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
-		double2 *out = reinterpret_cast<double2 *>(a.out + (long) s * a.out_ch_stride);
+		double2 *carry = reinterpret_cast<double2 *>(a.carry + (boff + s) * N);
+		double2 *out = reinterpret_cast<double2 *>(a.out + (boff + s) * a.out_ch_stride);
 		double2 c[8];
+		if (a.flags & INV_RAW) {
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				const int n = t + i * T;
+				const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
+				out[n] = make_double2(lo.x * scale, -lo.y * scale);
+				carry[n] = make_double2(hi.x * scale, -hi.y * scale);
+			}
+			return;
+		}
 		if (a.flags & INV_OUT) {
 #pragma unroll
 			for (int i = 0; i < 8; ++i) c[i] = carry[t + i * T];
@@ -539,6 +558,107 @@ __global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
 
 constexpr int FIR_T_BATCH = 4;
 
+// Bulk form of the whole convolution sum for calls that bring several whole blocks at once (offline rendering,
+// `dsp -b 65536`): Y_i = sum_{p<P} X_{j+i-p} H_p for the nb <= T new blocks i in ONE pass -- every FDL row
+// (P + T - 1 of them) and every filter row is streamed once for T outputs, the filter rows slide through a
+// T-deep register window.  Outputs i >= nb are computed on rows that do not exist yet and dropped.
+constexpr int FIR_NB_MAX = 8;
+
+struct MacBulkArgs {
+	const double2 *fdl;   // [s][rows][N]
+	const double2 *H;     // [s][P][N] or [P][N]
+	double2 *Y;           // [i][s][N]
+	int N, P, rows, n_sel, nb;
+	long j;               // first new block (its spectrum is in row j % rows)
+	long h_ch_stride;
+};
+
+template <int T, bool SHARED_H>
+__global__ void __launch_bounds__(256) k_fir_mac_bulk(MacBulkArgs a)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int s = blockIdx.y;
+	const double2 *fdl = a.fdl + (long) s * a.rows * a.N + k;
+	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
+	const bool dc = (k == 0);
+	const double2 zero = make_double2(0.0, 0.0);
+	double2 acc[T], hw[T];
+#define HROW(p) (((p) >= 0 && (p) < a.P) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
+	// step d = P-1 .. -(T-1): block m = j - d meets H_{d+i} for output i; window hw[i] = H_{d+i}
+	int d = a.P - 1;
+#pragma unroll
+	for (int i = 0; i < T; ++i) {
+		acc[i] = zero;
+		hw[i] = HROW(d + i);
+	}
+	int slot = (int) (((a.j - d) % a.rows + a.rows) % a.rows);   // row of X_{j-d}; grows by one per step
+#define XROW(e) __ldcs(&fdl[(long) ((slot + (e) >= a.rows) ? slot + (e) - a.rows : slot + (e)) * a.N])
+#define STEP(XV, HN)                                                          \
+	do {                                                                      \
+		_Pragma("unroll") for (int i = 0; i < T; ++i) {                       \
+			if (dc) {                                                         \
+				acc[i].x = fma(XV.x, hw[i].x, acc[i].x);                      \
+				acc[i].y = fma(XV.y, hw[i].y, acc[i].y);                      \
+			}                                                                 \
+			else {                                                            \
+				acc[i].x = fma(XV.x, hw[i].x, fma(-XV.y, hw[i].y, acc[i].x)); \
+				acc[i].y = fma(XV.x, hw[i].y, fma(XV.y, hw[i].x, acc[i].y));  \
+			}                                                                 \
+		}                                                                     \
+		_Pragma("unroll") for (int i = T - 1; i > 0; --i) hw[i] = hw[i - 1];  \
+		hw[0] = HN;                                                           \
+	} while (0)
+	const int steps = a.P + T - 1;
+	int n = 0;
+	for (; n + 4 <= steps; n += 4) {
+		const double2 x0 = XROW(0), x1 = XROW(1), x2 = XROW(2), x3 = XROW(3);
+		const double2 h0 = HROW(d - 1), h1 = HROW(d - 2), h2 = HROW(d - 3), h3 = HROW(d - 4);
+		STEP(x0, h0);
+		STEP(x1, h1);
+		STEP(x2, h2);
+		STEP(x3, h3);
+		d -= 4;
+		slot += 4;
+		if (slot >= a.rows) slot -= a.rows;
+	}
+	for (; n < steps; ++n) {
+		const double2 x0 = XROW(0);
+		const double2 h0 = HROW(d - 1);
+		STEP(x0, h0);
+		d -= 1;
+		slot = (slot + 1 == a.rows) ? 0 : slot + 1;
+	}
+#undef XROW
+#undef STEP
+#undef HROW
+#pragma unroll
+	for (int i = 0; i < T; ++i)
+		if (i < a.nb) a.Y[((long) i * a.n_sel + s) * a.N + k] = acc[i];
+}
+
+// bulk overlap-add + transpose: frame i B + f of the call = lo[i][s][f] + (i == 0 ? carry[s][f] : hi[i-1][s][f])
+__global__ void __launch_bounds__(256) k_fir_unstash_bulk(const double *__restrict__ lo, const double *__restrict__ hi, const double *__restrict__ carry,
+                                                          int B, double *__restrict__ out, long stride, const int *__restrict__ ch_map, int n_sel)
+{
+	__shared__ double tile[32][33];
+	const int f0 = blockIdx.x * 32, s0 = blockIdx.y * 32, i = blockIdx.z;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	const double *prev = (i == 0) ? carry : hi + (long) (i - 1) * n_sel * B;
+	const double *cur = lo + (long) i * n_sel * B;
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int s = s0 + r, f = f0 + tx;
+		tile[r][tx] = (s < n_sel && f < B) ? cur[(long) s * B + f] + prev[(long) s * B + f] : 0.0;
+	}
+	__syncthreads();
+	double *o = out + (long) i * B * stride;
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int f = f0 + r, s = s0 + tx;
+		if (f < B && s < n_sel) o[(long) f * stride + (ch_map ? ch_map[s] : s)] = tile[tx][r];
+	}
+}
+
 // general path: out[m] = pre[m] + pend(m) + sum_{r<=m} x[r] h0[m-r], m = pos+i; x = current level-0 block in the ring
 __global__ void k_fir_head(const double *hist, long hist_len, long blk_off, const double *pre, const double *h0, long h0_ch_stride,
                            PendArgs pend, double *out, long stride, const int *ch_map, int B, int pos, int seg)
@@ -603,22 +723,22 @@ static int configure_n()
 }
 
 template <int N>
-static int launch_fwd_n(const FwdArgs &a, cudaStream_t st)
+static int launch_fwd_n(const FwdArgs &a, cudaStream_t st, int nb)
 {
 	if (configure_n<N>()) return -1;
 	if (a.n_ch <= 0) return 0;
 	ProfScope prof("fir_fwd", st);
-	LAUNCH(k_fir_fwd<N>, ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	LAUNCH(k_fir_fwd<N>, dim3(ceil_div(a.n_ch, FftCfg<N>::CPB), nb), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
 	return 0;
 }
 
 template <int N>
-static int launch_inv_n(const InvArgs &a, cudaStream_t st)
+static int launch_inv_n(const InvArgs &a, cudaStream_t st, int nb)
 {
 	if (configure_n<N>()) return -1;
 	if (a.n_ch <= 0) return 0;
 	ProfScope prof("fir_inv", st);
-	LAUNCH(k_fir_inv<N>, ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	LAUNCH(k_fir_inv<N>, dim3(ceil_div(a.n_ch, FftCfg<N>::CPB), nb), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
 	return 0;
 }
 
@@ -646,8 +766,8 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 	default: set_error("unsupported FFT size %d", N_); return -1; \
 	}
 
-static int launch_fwd(int N, const FwdArgs &a, cudaStream_t st) { DISPATCH_N(N, launch_fwd_n, a, st) }
-static int launch_inv(int N, const InvArgs &a, cudaStream_t st) { DISPATCH_N(N, launch_inv_n, a, st) }
+static int launch_fwd(int N, const FwdArgs &a, cudaStream_t st, int nb = 1) { DISPATCH_N(N, launch_fwd_n, a, st, nb) }
+static int launch_inv(int N, const InvArgs &a, cudaStream_t st, int nb = 1) { DISPATCH_N(N, launch_inv_n, a, st, nb) }
 static int launch_level0(int N, const L0Args &a, cudaStream_t st) { DISPATCH_N(N, launch_level0_n, a, st) }
 
 static void launch_mac(const MacArgs &a, int n_sel, bool shared_h, const char *prof_name, cudaStream_t st)
@@ -704,6 +824,7 @@ int test_irfft(int B, int n_ch, const double *d_spec, double *d_out2B, cudaStrea
 // ------------------------------------------------------------------------------------------
 struct FirLevel {
 	int B = 0, P = 0;
+	int R = 0;                    // rows of the FDL ring per channel (P, or more when calls bring several blocks at once)
 	long tap0 = 0, tap1 = 0;      // taps [tap0, tap1) of the filter
 	const double2 *tw = nullptr, *ptw = nullptr;
 	double2 *fdl = nullptr, *H = nullptr;
@@ -751,6 +872,11 @@ struct FirOp : Op {
 	cudaEvent_t ev_batch[2] = { nullptr, nullptr }, ev_main2 = nullptr;
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
+	// bulk form (single-level plans): up to nb_max whole blocks of one call are transformed, multiplied and
+	// overlapped by one launch each
+	int nb_max = 1;
+	double2 *d_Ybulk = nullptr;
+	double *d_lo = nullptr, *d_hi = nullptr;
 	long abs_pos = 0;                    // frames consumed so far (level-0 block = abs_pos / B0, offset = abs_pos % B0)
 	bool pre_valid = false;
 
@@ -787,6 +913,7 @@ struct FirOp : Op {
 		dev_free(d_Y_side);
 		dev_free(d_ch_map); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp);
+		dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi);
 	}
 
 	int plan(long hint, cudaStream_t st)
@@ -818,10 +945,15 @@ struct FirOp : Op {
 		for (int l = 0; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			L.P = (int) ((L.tap1 - L.tap0 + L.B - 1) / L.B);
+			L.R = L.P;
+			if (n_levels == 1 && L.P > 2 && hint >= 2L * L.B && !(getenv("DSP_B200_FIR_NO_BULK") && getenv("DSP_B200_FIR_NO_BULK")[0] == '1')) {
+				nb_max = (int) ((hint / L.B < FIR_NB_MAX) ? hint / L.B : FIR_NB_MAX);
+				L.R = L.P + nb_max - 1;
+			}
 			L.tw = twiddles_2n(L.B);
 			L.ptw = twiddles_pass(L.B);
 			if (!L.tw || !L.ptw) return -1;
-			L.fdl = dev_alloc<double2>((size_t) n_sel * L.P * L.B);
+			L.fdl = dev_alloc<double2>((size_t) n_sel * L.R * L.B);
 			L.H = dev_alloc<double2>((size_t) nh * L.P * L.B);
 			L.carry = dev_alloc<double>((size_t) n_sel * L.B);
 			if (l > 0) L.pend = dev_alloc<double>((size_t) n_sel * L.B);
@@ -854,7 +986,13 @@ struct FirOp : Op {
 		}
 		// upper levels read their block from the ring on the side stream while the next block is already
 		// being stashed: keep two of the largest blocks
-		hist_len = (n_levels > 1) ? 2L * Bmax : Bmax;
+		hist_len = (n_levels > 1) ? 2L * Bmax : (long) nb_max * Bmax;
+		if (nb_max > 1) {
+			d_Ybulk = dev_alloc<double2>((size_t) nb_max * n_sel * B0, false);
+			d_lo = dev_alloc<double>((size_t) nb_max * n_sel * B0, false);
+			d_hi = dev_alloc<double>((size_t) nb_max * n_sel * B0, false);
+			if (!d_Ybulk || !d_lo || !d_hi) return -1;
+		}
 		d_hist = dev_alloc<double>((size_t) n_sel * hist_len);
 		d_ytmp = dev_alloc<double>((size_t) n_sel * B0);
 		d_pre = dev_alloc<double>((size_t) n_sel * B0);
@@ -902,7 +1040,7 @@ struct FirOp : Op {
 		for (int l = 0; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			L.blk = 0;
-			cudaMemsetAsync(L.fdl, 0, (size_t) n_sel * L.P * L.B * sizeof(double2), st);
+			cudaMemsetAsync(L.fdl, 0, (size_t) n_sel * L.R * L.B * sizeof(double2), st);
 			cudaMemsetAsync(L.carry, 0, (size_t) n_sel * L.B * sizeof(double), st);
 			if (L.pend) cudaMemsetAsync(L.pend, 0, (size_t) n_sel * L.B * sizeof(double), st);
 		}
@@ -913,8 +1051,8 @@ struct FirOp : Op {
 	void mac(FirLevel &L, int p0, int p1, long slot_blk, cudaStream_t st, double2 *Y = nullptr, const double2 *init = nullptr)
 	{
 		MacArgs m = {};
-		m.fdl = L.fdl; m.H = L.H; m.Y = Y ? Y : d_Y; m.init = init; m.N = L.B; m.P = L.P;
-		m.slot0 = (int) (slot_blk % L.P); m.p0 = p0; m.p1 = p1;
+		m.fdl = L.fdl; m.H = L.H; m.Y = Y ? Y : d_Y; m.init = init; m.N = L.B; m.P = L.R;   // the kernel's P: rows of the ring
+		m.slot0 = (int) (slot_blk % L.R); m.p0 = p0; m.p1 = p1;
 		m.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 		// the last level carries (almost) all the taps: it is the kernel the roofline line is about
 		launch_mac(m, n_sel, fc == 1, (&L == &lv[n_levels - 1]) ? "fir_mac" : "fir_mac_head", st);
@@ -926,7 +1064,7 @@ struct FirOp : Op {
 	{
 		FwdArgs f = {};
 		f.in = d_hist + (L.blk * L.B) % hist_len; f.ch_stride = hist_len; f.valid = L.B;
-		f.spec = L.fdl; f.spec_ch_stride = (long) L.P * L.B; f.slot = (int) (L.blk % L.P); f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
+		f.spec = L.fdl; f.spec_ch_stride = (long) L.R * L.B; f.slot = (int) (L.blk % L.R); f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
 		if (launch_fwd(L.B, f, st)) return -1;
 		mac(L, 0, L.P, L.blk, st);
 		InvArgs v = {};
@@ -963,9 +1101,9 @@ struct FirOp : Op {
 			any = true;
 			L0Args f = {};
 			f.in = d_hist + (L.blk * L.B) % hist_len; f.in_ch_stride = hist_len;
-			f.fdl = L.fdl; f.fdl_ch_stride = (long) L.P * L.B; f.fdl_rows = L.P;
+			f.fdl = L.fdl; f.fdl_ch_stride = (long) L.R * L.B; f.fdl_rows = L.R;
 			f.H = L.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
-			f.P = 1; f.slot = (int) (L.blk % L.P);
+			f.P = 1; f.slot = (int) (L.blk % L.R);
 			f.out = L.pend; f.out_ch_stride = L.B; f.carry = L.carry; f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
 			f.init = (L.tail && L.blk >= 1) ? d_Y_side : nullptr;   // Y of this block: launched one period ago, same stream
 			if (launch_level0(L.B, f, us)) return -1;
@@ -1031,6 +1169,51 @@ struct FirOp : Op {
 		}
 	}
 
+	// nb whole level-0 blocks of one call (single-level plans): stash all, ONE forward launch, ONE pass over
+	// the FDL and the filter spectra for all nb outputs (k_fir_mac_bulk), ONE inverse launch, ONE overlap/scatter
+	int bulk_blocks(int nb, const double *src, double *d, long dstride, const int *dmap, cudaStream_t st)
+	{
+		FirLevel &L = lv[0];
+		const long C = channels;
+		const long off = (abs_pos % hist_len);
+		// the new frames join the history ring (it holds nb_max blocks; at most one wrap)
+		{
+			const long total = (long) nb * B0, first = (total < hist_len - off) ? total : hist_len - off;
+			dim3 grid(ceil_div(first, 32), ceil_div(n_sel, 32));
+			LAUNCH(k_fir_stash, grid, 256, 0, st, src, C, d_ch_map, d_hist, hist_len, off, (int) first, n_sel);
+			if (first < total) {
+				dim3 grid2(ceil_div(total - first, 32), ceil_div(n_sel, 32));
+				LAUNCH(k_fir_stash, grid2, 256, 0, st, src + first * C, C, d_ch_map, d_hist, hist_len, 0L, (int) (total - first), n_sel);
+			}
+		}
+		FwdArgs f = {};
+		f.in = d_hist; f.ch_stride = hist_len; f.valid = B0;
+		f.spec = L.fdl; f.spec_ch_stride = (long) L.R * B0; f.slot = (int) (L.blk % L.R); f.tw = L.tw; f.ptw = L.ptw; f.n_ch = n_sel;
+		f.ring_len = hist_len; f.ring_off = off; f.slot_rows = L.R;
+		if (launch_fwd(B0, f, st, nb)) return -1;
+		{
+			MacBulkArgs b = {};
+			b.fdl = L.fdl; b.H = L.H; b.Y = d_Ybulk; b.N = B0; b.P = L.P; b.rows = L.R; b.n_sel = n_sel; b.nb = nb; b.j = L.blk;
+			b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * B0;
+			const int threads = (B0 < 256) ? B0 : 256;
+			dim3 grid(B0 / threads, n_sel);
+			ProfScope prof("fir_mac_bulk", st);
+			if (fc == 1) LAUNCH((k_fir_mac_bulk<FIR_NB_MAX, true>), grid, threads, 0, st, b);
+			else LAUNCH((k_fir_mac_bulk<FIR_NB_MAX, false>), grid, threads, 0, st, b);
+		}
+		InvArgs v = {};
+		v.Y = d_Ybulk; v.out = d_lo; v.out_ch_stride = B0; v.carry = d_hi; v.flags = INV_RAW; v.tw = L.tw; v.ptw = L.ptw; v.n_ch = n_sel;
+		if (launch_inv(B0, v, st, nb)) return -1;
+		{
+			dim3 grid(ceil_div(B0, 32), ceil_div(n_sel, 32), nb);
+			LAUNCH(k_fir_unstash_bulk, grid, 256, 0, st, d_lo, d_hi, L.carry, B0, d, dstride, dmap, n_sel);
+		}
+		CUDA_TRY(cudaMemcpyAsync(L.carry, d_hi + (size_t) (nb - 1) * n_sel * B0, (size_t) n_sel * B0 * sizeof(double), cudaMemcpyDeviceToDevice, st), return -1);
+		L.blk += nb;
+		pre_valid = false;
+		return 0;
+	}
+
 	int ensure_pre(cudaStream_t st)
 	{
 		if (pre_valid) return 0;
@@ -1073,6 +1256,14 @@ struct FirOp : Op {
 		while (done < frames) {
 			const double *src = in + done * C;
 			double *d = dst + done * dstride;
+			if (nb_max > 1 && abs_pos % B0 == 0 && frames - done >= 2L * B0) {
+				long nb = (frames - done) / B0;
+				if (nb > nb_max) nb = nb_max;
+				if (bulk_blocks((int) nb, src, d, dstride, dmap, st)) return -1;
+				abs_pos += nb * B0;
+				done += nb * B0;
+				continue;
+			}
 			const int pos = (int) (abs_pos % B0);
 			const long blk_off = (abs_pos - pos) % hist_len;
 			const int seg = (int) ((frames - done < B0 - pos) ? frames - done : B0 - pos);
@@ -1087,9 +1278,9 @@ struct FirOp : Op {
 				if (L0.P <= 2) {
 					L0Args f = {};
 					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
-					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.P * B0; f.fdl_rows = L0.P;
+					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.R * B0; f.fdl_rows = L0.R;
 					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
-					f.P = L0.P; f.slot = (int) (L0.blk % L0.P);
+					f.P = L0.P; f.slot = (int) (L0.blk % L0.R);
 					f.out = d_ytmp; f.out_ch_stride = B0; f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
 					if (launch_level0(B0, f, st)) return -1;
 					++L0.blk;

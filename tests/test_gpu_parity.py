@@ -277,10 +277,11 @@ def test_in_process_multi_gpu_sharding(gpu_lib):
     b.close()
 
 
-@pytest.mark.parametrize("block,taps", [(8192, 70000), (10000, 20000), (65536, 20000), (300, 40000)])
+@pytest.mark.parametrize("block,taps", [(8192, 70000), (10000, 20000), (65536, 20000), (300, 40000), (40000, 70000), (16384, 30000), (65536, 140000)])
 def test_fir_p_large_and_odd_blocks(gpu_lib, block, taps):
     """Partition = 8192 with many partitions (single level, three-kernel path), calls longer than the largest
-    partition, and a small odd block with a long filter (four levels)."""
+    partition (bulk form: several whole blocks per launch, with and without a ragged remainder), and a small odd
+    block with a long filter (four levels)."""
     from oracle import restate
     fs, C = 48000, 4
     rng = np.random.default_rng(block + taps)
@@ -293,4 +294,29 @@ def test_fir_p_large_and_odd_blocks(gpu_lib, block, taps):
     plan = ch.describe()[0]
     assert plan["planned"] == 1
     assert rms(got - want) <= RMS_TOL, (plan, rms(got - want))
+    ch.close()
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_fir_p_bulk_form_mixes_with_ragged_calls(gpu_lib, shared):
+    """A plan made for 32768-frame calls (4 blocks of 8192 per launch) fed with calls of every kind: bulk,
+    bulk + remainder, tiny, exactly one block, more blocks than the plan holds at once; shared and per-channel IR."""
+    from oracle import restate
+    fs, C, taps = 48000, 3, 50000
+    rng = np.random.default_rng(11)
+    h = restate.bench_ir(taps) if shared else np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
+    sizes = [32768, 100, 8192, 20000, 32768, 5, 16384 + 8192 - 105, 65536 + 3, 8192, 40000]
+    x = rng.standard_normal((sum(sizes), C)) * 0.2
+    want = restate.fir_stream(x, h)
+    ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=32768)
+    assert ch.describe()[0]["levels"] == [{"B": 8192, "P": 7}]
+    outs, pos = [], 0
+    for n in sizes:
+        outs.append(ch.run(x[pos:pos + n]).copy())
+        pos += n
+    got = np.concatenate(outs)
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+    ch.reset()
+    got2 = np.concatenate([ch.run(x[i:i + 32768]).copy() for i in range(0, 3 * 32768, 32768)])
+    assert rms(got2 - want[:3 * 32768]) <= RMS_TOL
     ch.close()
