@@ -279,20 +279,40 @@ def main():
     plan = [op for op in chain.describe() if op.get("op") == "fir"][0]
     lvl = plan["levels"][-1]
     h = 0 if a.shared_ir else 1
-    # with several levels, partition 0 of the last level is done inline by the fused kernel; the MAC streams the other P-1
-    mac_parts = lvl["P"] - 1 if len(plan["levels"]) > 1 else lvl["P"]
-    mac_bytes = C * lvl["B"] * 16.0 * (mac_parts * (1 + h) + 1)
+    # tail_pf = partitions of the last level summed inside its fused FFT kernel (0: no tail machinery, the plain
+    # three-kernel path; 1: an upper level carries the tail; 2: single level, the kernel sums partitions 0 and 1)
+    pf = int(plan.get("tail_pf", 0))
     tb = int(plan.get("t_batch", 0))
-    if tb:
-        # time-batched tail: every period k_fir_mac streams partitions 1..T plus the batched spectrum (read) and writes Y;
+    batch_bytes = 0.0
+    if pf == 0:
+        mac_parts = lvl["P"]
+        mac_bytes = C * lvl["B"] * 16.0 * (mac_parts * (1 + h) + 1)
+    elif tb:
+        # time-batched tail: every period k_fir_mac streams T partitions plus the batched spectrum (read) and writes Y;
         # every T periods k_fir_mac_batch streams the other FDL rows and filter rows once for T outputs
         mac_parts = tb
         mac_bytes = C * lvl["B"] * 16.0 * (tb * (1 + h) + 2)
-    batch_bytes = C * lvl["B"] * 16.0 * ((lvl["P"] - 2) + (lvl["P"] - tb - 1) * h + tb) if tb else 0.0
-    step_bytes = sum(C * L["B"] * 16.0 * (L["P"] * (1 + h) + 1) * (F / L["B"]) for L in plan["levels"])
-    if tb:
-        step_bytes = (C * plan["levels"][0]["B"] * 16.0 * (plan["levels"][0]["P"] * (1 + h) + 1)
-                      + (C * lvl["B"] * 16.0 * (1 + h + 1) + mac_bytes + batch_bytes / tb) * (F / lvl["B"]))
+        batch_bytes = C * lvl["B"] * 16.0 * ((lvl["P"] - pf - 1) + (lvl["P"] - pf - tb) * h + tb)
+    else:
+        mac_parts = lvl["P"] - pf
+        mac_bytes = C * lvl["B"] * 16.0 * (mac_parts * (1 + h) + 1)
+    tail_per_sample = (mac_bytes + (batch_bytes / tb if tb else 0.0)) / (C * lvl["B"])
+    step_bytes = tail_per_sample * C * F + sum(C * L["B"] * 16.0 * (min(L["P"], 2 if i == 0 else 1) * (1 + h)) * (F / L["B"])
+                                               for i, L in enumerate(plan["levels"]))
+
+    def step_budget():
+        """algorithmic HBM bytes per input sample of every kernel of a step"""
+        n_lv = len(plan["levels"])
+        per = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)                       # stash (read + write), unstash (y + pending sums + write)
+        for i, L in enumerate(plan["levels"]):
+            in_kernel = min(L["P"], 2 if i == 0 else 1)
+            has_init = pf and i == n_lv - 1
+            if pf == 0 and i == 0 and L["P"] > 2:
+                per += (8 + 16) + (16 + 8 + 8 + 8)                            # separate forward and inverse transforms
+                continue
+            per += 8 + 16 + 16 * (in_kernel - 1) + 16 * in_kernel * h + (16 if has_init else 0) + 8 + 8 + 8
+        return per + tail_per_sample
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -352,13 +372,10 @@ def main():
             roofline["batch_kernel"]["isolated_frac"] = roofline["batch_kernel"]["isolated_GBs"] / peak
         roofline["isolated_kernel_us"] = iso
         # all kernels of a step against the byte budget of the plan
-        B0 = plan["levels"][0]["B"]
-        per_sample = 16 + 32 + (8 + 16 * (2 * plan["levels"][0]["P"] - 1) * (1 if h else 0.5) + 16 + 8 + 8 + 8)
-        if len(plan["levels"]) > 1:
-            per_sample += (8 + 16 * h + 8 + 16 + 8 + 8) + mac_bytes / (C * lvl["B"]) + 16 + (batch_bytes / tb if tb else 0.0) / (C * lvl["B"])
+        per_sample = step_budget()
         roofline["step"] = {"algorithmic_bytes_per_sample": per_sample, "achieved": per_sample * C * F / (ms / steps * 1e-3) / 1e9,
                             "frac": per_sample * C * F / (ms / steps * 1e-3) / 1e9 / peak,
-                            "note": "every kernel of the step (stash, fused level 0, unstash, level-1 fused partition 0 + tail spectrum, MACs) over the step time"}
+                            "note": "every kernel of the step (stash, fused FFT kernels, unstash, tail MACs) over the step time"}
     chain.close()
     del chain
 

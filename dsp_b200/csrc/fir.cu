@@ -480,11 +480,12 @@ __global__ void __launch_bounds__(256) k_fir_mac(MacArgs a)
 	a.Y[(long) s * a.N + k] = make_double2((acc0.x + acc1.x) + (acc2.x + acc3.x), (acc0.y + acc1.y) + (acc2.y + acc3.y));
 }
 
-// Time-batched tail of the last level.  With V_j = sum_{p > T} X_{j-p} H_p (the part of block period j's
-// spectrum that only involves blocks at least T+1 periods old), one launch after block q completes produces
-// V_j for the T periods j = q+2 .. q+T+1 at once: every FDL row and every filter row is streamed ONCE for T
-// outputs (the filter rows slide through a T-deep register window), instead of once per output.
-// Y_t[k] = sum_{m=2}^{P-1} X_{q+2-m}[k] * H_{m+t}[k] over the (m, t) with T < m+t < P.
+// Time-batched tail of the last level.  With V_j = sum_{p >= pf+T} X_{j-p} H_p (the part of block period j's
+// spectrum that only involves blocks at least pf+T periods old; pf = partitions summed inside the fused FFT
+// kernel), one launch after block q completes produces V_j for the T periods j = q+pf+1 .. q+pf+T at once: every
+// FDL row and every filter row is streamed ONCE for T outputs (the filter rows slide through a T-deep
+// register window), instead of once per output.
+// Y_t[k] = sum_{m=pf+1}^{P-1} X_{q+pf+1-m}[k] * H_{m+t}[k] over the (m, t) with pf+T <= m+t < P.
 struct MacBatchArgs {
 	const double2 *fdl;   // [s][P][N]
 	const double2 *H;     // [s][P][N] or [P][N]
@@ -493,6 +494,7 @@ struct MacBatchArgs {
 	long q;               // block that just completed
 	int n_slots;
 	long h_ch_stride;
+	int pf;               // partitions 0..pf-1 are summed by the level's fused FFT kernel (1: upper levels, 2: level 0)
 };
 
 template <int T, bool SHARED_H>
@@ -505,13 +507,13 @@ __global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
 	const bool dc = (k == 0);
 	const double2 zero = make_double2(0.0, 0.0);
 	double2 acc[T], hw[T];
-#define HROW(p) (((p) > T && (p) < a.P) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
+#define HROW(p) (((p) >= T + a.pf && (p) < a.P) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
 #pragma unroll
 	for (int t = 0; t < T; ++t) {
 		acc[t] = zero;
-		hw[t] = HROW(2 + t);
+		hw[t] = HROW(a.pf + 1 + t);
 	}
-	int slot = (int) ((a.q + 2 - 2) % a.P);   // row of X_{q+2-m} for m = 2
+	int slot = (int) (a.q % a.P);   // row of X_{q+pf+1-m} for m = pf+1
 #define XROW(d) __ldcs(&fdl[(long) ((slot - (d) < 0) ? slot - (d) + a.P : slot - (d)) * a.N])
 #define STEP(XV, HN)                                                          \
 	do {                                                                      \
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
 		_Pragma("unroll") for (int t = 0; t + 1 < T; ++t) hw[t] = hw[t + 1];  \
 		hw[T - 1] = HN;                                                       \
 	} while (0)
-	int m = 2;
+	int m = a.pf + 1;
 	for (; m + 4 <= a.P; m += 4) {
 		// eight independent 16-byte loads in flight per thread, as in k_fir_mac
 		const double2 x0 = XROW(0), x1 = XROW(1), x2 = XROW(2), x3 = XROW(3);
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
 #undef HROW
 #pragma unroll
 	for (int t = 0; t < T; ++t) {
-		const long j = a.q + 2 + t;
+		const long j = a.q + a.pf + 1 + t;
 		a.V[((j % a.n_slots) * a.n_sel + s) * (long) a.N + k] = acc[t];
 	}
 }
@@ -860,7 +862,9 @@ struct FirOp : Op {
 	int *d_ch_map = nullptr;
 	double *d_hist = nullptr, *d_ytmp = nullptr, *d_pre = nullptr, *d_h0 = nullptr;
 	double2 *d_Y = nullptr;              // [n_sel][max B]
-	double2 *d_Y_side = nullptr;         // [n_sel][B last]: the tail spectrum of the next block period (side stream)
+	double2 *d_Y_side = nullptr;         // [n_sel][B last]: the tail spectrum of the next block period (side stream); two of them when level 0 has the tail
+	int tail_pf = 0;                     // 0: no tail; 1: tail on an upper level; 2: tail on level 0 (single-level plan, fused kernel sums p = 0, 1)
+	cudaEvent_t ev_tail[2] = { nullptr, nullptr };
 	double *d_ring = nullptr, *d_ltmp = nullptr;
 	// side stream: the upper levels' partition-0 kernels and the last level's tail MAC overlap the main stream
 	cudaStream_t side = nullptr;
@@ -889,7 +893,7 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d}", t_batch);
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"tail_pf\":%d,\"bulk\":%d}", t_batch, tail_pf, nb_max);
 		return buf;
 	}
 
@@ -906,6 +910,8 @@ struct FirOp : Op {
 		for (cudaEvent_t e : ev_batch)
 			if (e) cudaEventDestroy(e);
 		if (ev_main2) cudaEventDestroy(ev_main2);
+		for (cudaEvent_t e : ev_tail)
+			if (e) cudaEventDestroy(e);
 		dev_free(d_V);
 		if (ev_main) cudaEventDestroy(ev_main);
 		if (ev_urgent) cudaEventDestroy(ev_urgent);
@@ -924,7 +930,13 @@ struct FirOp : Op {
 		const long T = filter_frames;
 		// level plan (see the header comment)
 		n_levels = 0;
-		if (!multilevel || T <= 2L * B0 || B0 >= FIR_MAX_B) {
+		// Partitions grow up to `cap`: beyond it the larger transforms (one CTA per SM, twice the passes) cost
+		// more than the filter traffic they save once the tail is time-batched (measured)
+		long cap = 4096;
+		if (const char *e = getenv("DSP_B200_FIR_LEVEL_CAP")) cap = atol(e);
+		if (cap < B0) cap = B0;
+		if (cap > FIR_MAX_B) cap = FIR_MAX_B;
+		if (!multilevel || T <= 2L * B0 || B0 >= cap) {
 			lv[0].B = B0; lv[0].tap0 = 0; lv[0].tap1 = T;
 			n_levels = 1;
 		}
@@ -935,7 +947,7 @@ struct FirOp : Op {
 			while (n_levels < FIR_MAX_LEVELS) {
 				FirLevel &L = lv[n_levels++];
 				L.B = (int) B; L.tap0 = B;
-				if (B >= FIR_MAX_B || T <= 2 * B || n_levels == FIR_MAX_LEVELS) { L.tap1 = T; break; }
+				if (B >= cap || T <= 2 * B || n_levels == FIR_MAX_LEVELS) { L.tap1 = T; break; }
 				L.tap1 = 2 * B;
 				B *= 2;
 			}
@@ -958,19 +970,26 @@ struct FirOp : Op {
 			L.carry = dev_alloc<double>((size_t) n_sel * L.B);
 			if (l > 0) L.pend = dev_alloc<double>((size_t) n_sel * L.B);
 			if (!L.fdl || !L.H || !L.carry || (l > 0 && !L.pend)) return -1;
-			if (l > 0 && !side) {
+			// the last level's partitions beyond those its fused kernel sums form the "tail"; a single level keeps
+			// partitions 0 and 1 in the kernel (pf = 2), an upper level only partition 0 (pf = 1)
+			const int pf = (l == 0) ? 2 : 1;
+			const bool has_tail = (l == n_levels - 1) && L.P > pf && (l > 0 || (nb_max == 1 && multilevel));
+			if ((l > 0 || has_tail) && !side) {
 				int lo = 0, hi = 0;
 				cudaDeviceGetStreamPriorityRange(&lo, &hi);
 				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_urgent, cudaEventDisableTiming), return -1);
+				CUDA_TRY(cudaEventCreateWithFlags(&ev_tail[0], cudaEventDisableTiming), return -1);
+				CUDA_TRY(cudaEventCreateWithFlags(&ev_tail[1], cudaEventDisableTiming), return -1);
 			}
-			if (l > 0 && l == n_levels - 1 && L.P > 1) {
+			if (has_tail) {
 				L.tail = true;
-				d_Y_side = dev_alloc<double2>((size_t) n_sel * L.B);
+				tail_pf = pf;
+				d_Y_side = dev_alloc<double2>((size_t) pf * n_sel * L.B);
 				if (!d_Y_side) return -1;
 				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
-				if (L.P >= 2 * FIR_T_BATCH + 2 && !(nb && nb[0] == '1')) {
+				if (L.P >= 2 * FIR_T_BATCH + pf + 1 && !(nb && nb[0] == '1')) {
 					t_batch = FIR_T_BATCH;
 					d_V = dev_alloc<double2>((size_t) 2 * t_batch * n_sel * L.B);
 					if (!d_V) return -1;
@@ -1113,7 +1132,7 @@ struct FirOp : Op {
 		CUDA_TRY(cudaEventRecord(ev_urgent, us), return -1);
 		urgent_pending = (us != st);
 		FirLevel &L = lv[n_levels - 1];
-		if (L.tail && abs_pos % L.B == 0) {
+		if (L.tail && tail_pf == 1 && abs_pos % L.B == 0) {
 			const long q1 = L.blk;   // Y_{q+1}, q = the block that just completed
 			if (t_batch > 0) {
 				// Y_j = U_j + V_j, j = q1: U_j = sum_{1<=p<=T} X_{j-p} H_p now, V_j from the batch launched at
@@ -1134,6 +1153,7 @@ struct FirOp : Op {
 				MacBatchArgs b = {};
 				b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
 				b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+				b.pf = 1;
 				const int threads = (L.B < 256) ? L.B : 256;
 				dim3 grid(L.B / threads, n_sel);
 				{
@@ -1143,6 +1163,49 @@ struct FirOp : Op {
 				}
 				CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
 			}
+		}
+		return 0;
+	}
+
+	// Single-level plans: after block q of level 0 has entered the FDL (fused kernel or general path), the part
+	// of block q+2's spectrum that is already known, Y_{q+2} = sum_{p>=2} X_{q+2-p} H_p, is accumulated on the
+	// side stream -- a whole block period ahead of the fused kernel that adds X_{q+2} H_0 + X_{q+1} H_1 to it.
+	// With time-batching, V_j = sum_{p>=T+2} (T periods per launch, second side stream) is its starting value.
+	int advance_tail0(cudaStream_t st)
+	{
+		FirLevel &L = lv[0];
+		const bool serial = g_fir_serialize.load(std::memory_order_relaxed) != 0;
+		cudaStream_t ts = serial ? st : side, bs = serial ? st : side2;
+		const long q = L.blk - 1, j = q + 2;
+		double2 *Y = d_Y_side + (size_t) (j & 1) * n_sel * L.B;
+		if (!serial) {
+			CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
+			CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
+		}
+		if (t_batch > 0) {
+			const int T = t_batch;
+			if (j >= 3) {
+				const long qb = ((j - 3) / T) * T;   // V_j comes from the batch launched after block qb
+				CUDA_TRY(cudaStreamWaitEvent(ts, ev_batch[(qb / T) & 1], 0), return -1);
+			}
+			mac(L, 2, T + 2, j, ts, Y, d_V + (size_t) (j % (2 * T)) * n_sel * L.B);
+		}
+		else mac(L, 2, L.P, j, ts, Y);
+		CUDA_TRY(cudaEventRecord(ev_tail[j & 1], ts), return -1);
+		if (t_batch > 0 && q % t_batch == 0) {
+			if (!serial) CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
+			MacBatchArgs b = {};
+			b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
+			b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+			b.pf = 2;
+			const int threads = (L.B < 256) ? L.B : 256;
+			dim3 grid(L.B / threads, n_sel);
+			{
+				ProfScope prof("fir_mac_batch", bs);
+				if (fc == 1) LAUNCH((k_fir_mac_batch<FIR_T_BATCH, true>), grid, threads, 0, bs, b);
+				else LAUNCH((k_fir_mac_batch<FIR_T_BATCH, false>), grid, threads, 0, bs, b);
+			}
+			CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
 		}
 		return 0;
 	}
@@ -1275,13 +1338,18 @@ struct FirOp : Op {
 			}
 			if (pos == 0 && seg == B0) {
 				// fast path: one whole aligned block
-				if (L0.P <= 2) {
+				if (L0.P <= 2 || tail_pf == 2) {
 					L0Args f = {};
 					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
 					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.R * B0; f.fdl_rows = L0.R;
 					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
-					f.P = L0.P; f.slot = (int) (L0.blk % L0.R);
+					f.P = (L0.P < 2) ? L0.P : 2; f.slot = (int) (L0.blk % L0.R);
 					f.out = d_ytmp; f.out_ch_stride = B0; f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
+					if (tail_pf == 2 && L0.blk >= 2) {
+						// Y of this block was launched two blocks ago (advance_tail0)
+						CUDA_TRY(cudaStreamWaitEvent(st, ev_tail[L0.blk & 1], 0), return -1);
+						f.init = d_Y_side + (size_t) (L0.blk & 1) * n_sel * B0;
+					}
 					if (launch_level0(B0, f, st)) return -1;
 					++L0.blk;
 				}
@@ -1304,7 +1372,7 @@ struct FirOp : Op {
 			}
 			abs_pos += seg;
 			done += seg;
-			if (abs_pos % B0 == 0 && advance_upper_levels(st)) return -1;
+			if (abs_pos % B0 == 0 && ((tail_pf == 2) ? advance_tail0(st) : advance_upper_levels(st))) return -1;
 		}
 
 		if (latency > 0) {

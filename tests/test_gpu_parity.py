@@ -320,3 +320,29 @@ def test_fir_p_bulk_form_mixes_with_ragged_calls(gpu_lib, shared):
     got2 = np.concatenate([ch.run(x[i:i + 32768]).copy() for i in range(0, 3 * 32768, 32768)])
     assert rms(got2 - want[:3 * 32768]) <= RMS_TOL
     ch.close()
+
+
+@pytest.mark.parametrize("block,taps,shared", [(4096, 60000, True), (4096, 131072, False), (8192, 100000, False), (4096, 13000, True)])
+def test_fir_p_single_level_with_tail(gpu_lib, block, taps, shared):
+    """Blocks of the largest partition size the planner uses (4096; or the block itself above that): ONE level,
+    its fused kernel sums partitions 0 and 1, the rest arrives as a spectrum accumulated two blocks ahead
+    (time-batched when there are enough partitions; 13000 taps = 4 partitions: not batched).  Aligned calls,
+    then the same stream in random cuts (general path and fused path interleave on the same state)."""
+    from oracle import restate
+    fs, C = 48000, 3
+    rng = np.random.default_rng(block + taps)
+    h = restate.bench_ir(taps) if shared else np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
+    N = 14 * block + 1234
+    x = rng.standard_normal((N, C)) * 0.2
+    want = restate.fir_stream(x, h)
+    ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=block)
+    plan = ch.describe()[0]
+    assert len(plan["levels"]) == 1 and plan["tail_pf"] == 2, plan
+    assert (plan["t_batch"] > 0) == (plan["levels"][0]["P"] >= 11), plan
+    got = np.concatenate([ch.run(x[i:i + block]).copy() for i in range(0, N, block)])
+    assert rms(got - want) <= RMS_TOL, (plan, rms(got - want))
+    ch.reset()
+    cuts = sorted(set([0, N, 3 * block, 4 * block, 5 * block, 9 * block] + list(rng.integers(1, N, 12))))
+    got2 = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
+    assert rms(got2 - want) <= RMS_TOL, (plan, rms(got2 - want))
+    ch.close()
