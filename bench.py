@@ -266,9 +266,6 @@ def main():
     launches = dsp_b200.kernel_launches() - launches0
     dsp_b200.profile_enable(False)
     ms = reduce_max(e0.elapsed_time(e1))
-    mac_ms, mac_n = dsp_b200.profile_read("fir_mac")
-    fwd_ms, fwd_n = dsp_b200.profile_read("fir_fwd")
-    inv_ms, inv_n = dsp_b200.profile_read("fir_inv")
     total_samples = float(world) * C * F * steps
     value = total_samples / (ms * 1e-3) / 1e6
     checksum = float(d_out.abs().sum().item())
@@ -301,17 +298,21 @@ def main():
                                                for i, L in enumerate(plan["levels"]))
 
     def step_budget():
-        """algorithmic HBM bytes per input sample of every kernel of a step"""
+        """algorithmic HBM bytes per input sample of every kernel of a step: total and per kernel"""
         n_lv = len(plan["levels"])
-        per = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)                       # stash (read + write), unstash (y + pending sums + write)
+        parts = {"stash_unstash": 0.0, "fir_level0": 0.0, "fir_fwd_inv": 0.0, "fir_mac": mac_bytes / (C * lvl["B"]),
+                 "fir_mac_batch": (batch_bytes / tb if tb else 0.0) / (C * lvl["B"])}
+        direct = n_lv == 1 and pf != 0 or (n_lv == 1 and lvl["P"] <= 2)     # fused kernel reads/writes the interleaved block itself
+        if not direct:
+            parts["stash_unstash"] = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)   # stash (read + write), unstash (y + pending sums + write)
         for i, L in enumerate(plan["levels"]):
             in_kernel = min(L["P"], 2 if i == 0 else 1)
             has_init = pf and i == n_lv - 1
             if pf == 0 and i == 0 and L["P"] > 2:
-                per += (8 + 16) + (16 + 8 + 8 + 8)                            # separate forward and inverse transforms
+                parts["fir_fwd_inv"] += (8 + 16) + (16 + 8 + 8 + 8)           # separate forward and inverse transforms
                 continue
-            per += 8 + 16 + 16 * (in_kernel - 1) + 16 * in_kernel * h + (16 if has_init else 0) + 8 + 8 + 8
-        return per + tail_per_sample
+            parts["fir_level0"] += 8 + 16 + 16 * (in_kernel - 1) + 16 * in_kernel * h + (16 if has_init else 0) + 8 + 8 + 8
+        return sum(parts.values()), parts
 
     peaks = {}
     try:
@@ -322,33 +323,38 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "fir_mac:C%d:B%d:P%d:h%d" % (C, lvl["B"], mac_parts, h)
-        traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+        key = "step:C%d:F%d:taps%d:h%d" % (C, F, a.taps, h)
+        traffic = tr.get(key, {}).get("dram_bytes_per_step")
     except Exception:
         pass
     roofline = None
-    head_ms, head_n = dsp_b200.profile_read("fir_mac_head")
-    batch_ms, batch_n = dsp_b200.profile_read("fir_mac_batch")
-    if mac_n > 0:
-        mac_avg_s = mac_ms / mac_n * 1e-3
-        ach = mac_bytes / mac_avg_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_fir_mac (level B=%d, %d of %d partitions)" % (lvl["B"], mac_parts, lvl["P"]), "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+    per_sample, parts = step_budget()
+    step_s = ms / steps * 1e-3
+    in_loop = {}
+    for nme in ("fir_level0", "fir_mac", "fir_mac_batch", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk"):
+        t_ms, n_l = dsp_b200.profile_read(nme)
+        if n_l:
+            in_loop[nme] = (t_ms / n_l * 1e3, n_l / float(steps))
+    if step_s > 0:
+        ach = per_sample * C * F / step_s / 1e9
+        roofline = {"bound": "hbm",
+                    "kernel": "one step = every kernel of the chain for one block (%s), on three concurrent streams" % ", ".join("k_" + k for k in in_loop),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                    "algorithmic_bytes_per_launch": mac_bytes, "avg_launch_us": mac_avg_s * 1e6, "launches": mac_n,
-                    "share_of_step": mac_ms / ms if ms > 0 else None,
-                    "partition_levels": plan["levels"], "t_batch": tb, "mac_bytes_per_step_all_levels": step_bytes,
-                    "batch_kernel": ({"kernel": "k_fir_mac_batch", "algorithmic_bytes_per_launch": batch_bytes, "avg_launch_us": batch_ms / batch_n * 1e3,
-                                      "achieved_GBs": batch_bytes / (batch_ms / batch_n * 1e-3) / 1e9, "launches": batch_n} if batch_n else None),
-                    "other_kernels_us_per_step": {"k_fir_fwd": fwd_ms / steps * 1e3, "k_fir_inv": inv_ms / steps * 1e3,
-                                                  "k_fir_mac_head": head_ms / steps * 1e3, "k_fir_level0": dsp_b200.profile_read("fir_level0")[0] / steps * 1e3, "k_fir_mac": mac_ms / steps * 1e3}}
+                    "algorithmic_bytes_per_step": per_sample * C * F, "algorithmic_bytes_per_sample": per_sample,
+                    "bytes_per_sample_by_kernel": parts, "avg_step_us": step_s * 1e6,
+                    "partition_levels": plan["levels"], "t_batch": tb, "tail_pf": pf,
+                    "note": "achieved = algorithmic bytes of all kernels of a step / measured step time (CUDA events over the timed loop). "
+                            "The kernels of a step run concurrently on three streams and time-slice the GPU, so a single kernel's "
+                            "event-bracketed duration inside the loop is not its own speed; `kernels` gives each kernel timed alone "
+                            "(side streams folded into one) next to its in-loop figure."}
     # isolated kernel durations: a short extra pass with the side streams folded into the caller's stream
     iso = {}
     dsp_b200.debug_serialize(True)
     for i in range(2 * 8):
         chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
     torch.cuda.synchronize()
-    names = ("fir_mac", "fir_mac_batch", "fir_level0", "fir_inv")
+    names = ("fir_mac", "fir_mac_batch", "fir_level0", "fir_inv", "fir_fwd", "fir_mac_bulk")
     for nme in names:
         dsp_b200.profile_read(nme)
     dsp_b200.profile_enable(True)
@@ -362,20 +368,17 @@ def main():
         if n_l:
             iso[nme] = t_ms / n_l * 1e3
     if roofline is not None:
-        if "fir_mac" in iso:
-            roofline["isolated"] = {"avg_launch_us": iso["fir_mac"], "achieved": mac_bytes / (iso["fir_mac"] * 1e-6) / 1e9,
-                                    "frac": mac_bytes / (iso["fir_mac"] * 1e-6) / 1e9 / peak,
-                                    "note": "same kernel with the side streams folded into one stream (no concurrent kernels competing for HBM)"}
-        if tb and "fir_mac_batch" in iso and roofline.get("batch_kernel"):
-            roofline["batch_kernel"]["isolated_us"] = iso["fir_mac_batch"]
-            roofline["batch_kernel"]["isolated_GBs"] = batch_bytes / (iso["fir_mac_batch"] * 1e-6) / 1e9
-            roofline["batch_kernel"]["isolated_frac"] = roofline["batch_kernel"]["isolated_GBs"] / peak
-        roofline["isolated_kernel_us"] = iso
-        # all kernels of a step against the byte budget of the plan
-        per_sample = step_budget()
-        roofline["step"] = {"algorithmic_bytes_per_sample": per_sample, "achieved": per_sample * C * F / (ms / steps * 1e-3) / 1e9,
-                            "frac": per_sample * C * F / (ms / steps * 1e-3) / 1e9 / peak,
-                            "note": "every kernel of the step (stash, fused FFT kernels, unstash, tail MACs) over the step time"}
+        alg = {"fir_level0": parts["fir_level0"] * C * plan["levels"][0]["B"] if len(plan["levels"]) == 1 else None,
+               "fir_mac": mac_bytes, "fir_mac_batch": batch_bytes if tb else None}
+        kern = {}
+        for nme in sorted(set(list(iso) + list(in_loop))):
+            e = {"launches_per_step": in_loop.get(nme, (None, 0.0))[1], "in_step_event_us": in_loop.get(nme, (None, 0.0))[0],
+                 "alone_us": iso.get(nme), "algorithmic_bytes_per_launch": alg.get(nme)}
+            if e["alone_us"] and e["algorithmic_bytes_per_launch"]:
+                e["alone_GBs"] = e["algorithmic_bytes_per_launch"] / (e["alone_us"] * 1e-6) / 1e9
+                e["alone_frac"] = e["alone_GBs"] / peak
+            kern["k_" + nme] = e
+        roofline["kernels"] = kern
     chain.close()
     del chain
 

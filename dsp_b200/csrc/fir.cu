@@ -268,6 +268,14 @@ struct L0Args {
 	const double2 *tw, *ptw;
 	int n_ch;
 	const double2 *init;     // [s][N] spectrum added to S before the inverse transform (NULL: none)
+	// direct form (single-level plans): read the block from / write the result to the caller's interleaved
+	// buffers instead of the per-channel staging copies (no stash / unstash kernels)
+	const double *xin;       // NULL: use `in`
+	long xin_stride;
+	const int *xin_map;      // channel of selected channel s (NULL: s)
+	double *yout;            // NULL: use `out`
+	long yout_stride;
+	const int *yout_map;
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p)
@@ -298,10 +306,22 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 	double2 *buf = smem + (size_t) g * FftCfg<N>::STRIDE;
 
 	if (active) {
-		const double2 *x = reinterpret_cast<const double2 *>(a.in + (long) s * a.in_ch_stride);
 		double2 v[8];
+		if (a.xin) {
+			// frames 2n, 2n+1 of this channel: 8-byte loads one row apart (the 3 neighbouring channels' CTAs use the
+			// rest of each sector at about the same time: L2 serves them)
+			const double *xc = a.xin + (a.xin_map ? a.xin_map[s] : s);
 #pragma unroll
-		for (int i = 0; i < 8; ++i) v[i] = x[t + i * T];
+			for (int i = 0; i < 8; ++i) {
+				const long n2 = 2L * (t + i * T);
+				v[i] = make_double2(xc[n2 * a.xin_stride], xc[(n2 + 1) * a.xin_stride]);
+			}
+		}
+		else {
+			const double2 *x = reinterpret_cast<const double2 *>(a.in + (long) s * a.in_ch_stride);
+#pragma unroll
+			for (int i = 0; i < 8; ++i) v[i] = x[t + i * T];
+		}
 		// what the middle and the last phase will read from HBM: start it moving towards L2 now, so that it
 		// arrives while the first transform runs (the CTA's warps all sit in the same phase, nothing else hides it)
 		{
@@ -402,6 +422,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 		const double scale = 1.0 / N;
 		double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
 		double2 *out = reinterpret_cast<double2 *>(a.out + (long) s * a.out_ch_stride);
+		double *yc = a.yout ? a.yout + (a.yout_map ? a.yout_map[s] : s) : nullptr;
 		double2 c[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) c[i] = carry[t + i * T];
@@ -409,7 +430,12 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) k_fir_level0(L0Args a)
 		for (int i = 0; i < 8; ++i) {
 			const int n = t + i * T;
 			const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
-			out[n] = make_double2(fma(lo.x, scale, c[i].x), fma(-lo.y, scale, c[i].y));
+			const double2 y = make_double2(fma(lo.x, scale, c[i].x), fma(-lo.y, scale, c[i].y));
+			if (yc) {
+				yc[2L * n * a.yout_stride] = y.x;
+				yc[(2L * n + 1) * a.yout_stride] = y.y;
+			}
+			else out[n] = y;
 			carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 		}
 	}
@@ -879,6 +905,7 @@ struct FirOp : Op {
 	// bulk form (single-level plans): up to nb_max whole blocks of one call are transformed, multiplied and
 	// overlapped by one launch each
 	int nb_max = 1;
+	bool direct_io = !(getenv("DSP_B200_FIR_NO_DIRECT") && getenv("DSP_B200_FIR_NO_DIRECT")[0] == '1');
 	double2 *d_Ybulk = nullptr;
 	double *d_lo = nullptr, *d_hi = nullptr;
 	long abs_pos = 0;                    // frames consumed so far (level-0 block = abs_pos / B0, offset = abs_pos % B0)
@@ -1175,12 +1202,17 @@ struct FirOp : Op {
 	{
 		FirLevel &L = lv[0];
 		const bool serial = g_fir_serialize.load(std::memory_order_relaxed) != 0;
-		cudaStream_t ts = serial ? st : side, bs = serial ? st : side2;
+		// The per-block MAC runs on the side stream, time-slicing with the next fused kernel (measured: 107 us per
+		// step against 120 with the MAC queued behind the fused kernel on the caller's stream, where it runs alone
+		// at 0.95 of the HBM peak -- DSP_B200_FIR_TAIL_MAIN=1 selects that for measurements).
+		static const int tail_main = getenv("DSP_B200_FIR_TAIL_MAIN") ? atoi(getenv("DSP_B200_FIR_TAIL_MAIN")) : -1;
+		const bool on_main = serial || tail_main > 0;
+		cudaStream_t ts = on_main ? st : side, bs = serial ? st : side2;
 		const long q = L.blk - 1, j = q + 2;
 		double2 *Y = d_Y_side + (size_t) (j & 1) * n_sel * L.B;
 		if (!serial) {
 			CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
-			CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
+			if (!on_main) CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
 		}
 		if (t_batch > 0) {
 			const int T = t_batch;
@@ -1331,8 +1363,10 @@ struct FirOp : Op {
 			const long blk_off = (abs_pos - pos) % hist_len;
 			const int seg = (int) ((frames - done < B0 - pos) ? frames - done : B0 - pos);
 			const PendArgs pend = pend_args(abs_pos);
+			// single-level plans: the fused kernel reads the caller's block and writes the caller's result itself
+			const bool direct = direct_io && n_levels == 1 && pos == 0 && seg == B0 && (L0.P <= 2 || tail_pf == 2);
 			// the new frames join the history ring
-			{
+			if (!direct) {
 				dim3 grid(ceil_div(seg, 32), ceil_div(n_sel, 32));
 				LAUNCH(k_fir_stash, grid, 256, 0, st, src, C, d_ch_map, d_hist, hist_len, blk_off + pos, seg, n_sel);
 			}
@@ -1341,6 +1375,10 @@ struct FirOp : Op {
 				if (L0.P <= 2 || tail_pf == 2) {
 					L0Args f = {};
 					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
+					if (direct) {
+						f.xin = src; f.xin_stride = C; f.xin_map = d_ch_map;
+						f.yout = d; f.yout_stride = dstride; f.yout_map = dmap;
+					}
 					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.R * B0; f.fdl_rows = L0.R;
 					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
 					f.P = (L0.P < 2) ? L0.P : 2; f.slot = (int) (L0.blk % L0.R);
@@ -1354,8 +1392,10 @@ struct FirOp : Op {
 					++L0.blk;
 				}
 				else if (level_block(L0, d_ytmp, B0, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
-				side_wait(abs_pos, st);
-				LAUNCH(k_fir_unstash, tgrid_full, 256, 0, st, d_ytmp, (long) B0, pend, d, dstride, dmap, B0, n_sel);
+				if (!direct) {
+					side_wait(abs_pos, st);
+					LAUNCH(k_fir_unstash, tgrid_full, 256, 0, st, d_ytmp, (long) B0, pend, d, dstride, dmap, B0, n_sel);
+				}
 				pre_valid = false;
 			}
 			else {

@@ -13,10 +13,9 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 if [ "$mode" = "full" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fir_mac -s 10 -c 2 -o gpurun_out/prof_fir_mac -f \
+  # every k_fir_* launch of 8 steps (8 fused level-0, 8 per-block MACs, 2 batched MACs): per-kernel DRAM traffic for traffic.json
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fir_ -s 45 -c 18 -o gpurun_out/prof_fir_step -f \
       python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fir_level0 -s 12 -c 3 -o gpurun_out/prof_level0 -f \
-      python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_level0.log 2>&1
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_bq_cascade -s 3 -c 1 -o gpurun_out/prof_bq -f \
       python scripts/run_biquad.py > gpurun_out/ncu_bq.log 2>&1
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_rs_mma -s 3 -c 1 -o gpurun_out/prof_rs -f \

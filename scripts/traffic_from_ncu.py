@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""profiles/traffic.json entry for the headline step from an `ncu --set full` capture of the k_fir_* kernels
+(gpurun_out/prof_fir_step.ncu-rep, see scripts/gpu_round.sh): DRAM bytes (read + write) per launch of each
+kernel, times its launches per step as counted in the same capture window.
+
+    python scripts/traffic_from_ncu.py [C F taps h]      # defaults: 256 4096 131072 1
+"""
+import collections, csv, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rep = os.path.join(ROOT, "gpurun_out", "prof_fir_step.ncu-rep")
+C, F, taps, h = (int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (256, 4096, 131072, 1)))
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[0]
+ki, ri, wi, ti = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+units = rows[1]
+scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+per = collections.OrderedDict()
+for r in rows[2:]:
+    name = r[ki].split("(")[0].replace("void ", "").replace("dspb200::", "")
+    b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+    per.setdefault(name, []).append((b, float(r[ti])))
+n_l0 = sum(len(v) for k, v in per.items() if k.startswith("k_fir_level0"))   # one fused level-0 launch per step
+out = {"kernels": {}, "window_steps": n_l0}
+total = 0.0
+for k, v in per.items():
+    avg = sum(b for b, _ in v) / len(v)
+    out["kernels"][k] = {"dram_bytes_per_launch": avg, "launches_in_window": len(v), "launches_per_step": len(v) / max(n_l0, 1),
+                         "avg_us_under_ncu": sum(t for _, t in v) / len(v)}
+    total += avg * len(v) / max(n_l0, 1)
+out["dram_bytes_per_step"] = total
+out["source"] = "ncu --set full --clock-control none -k regex:k_fir_ (gpurun_out/prof_fir_step.ncu-rep); dram__bytes_read.sum + dram__bytes_write.sum"
+path = os.path.join(ROOT, "profiles", "traffic.json")
+tr = json.load(open(path)) if os.path.exists(path) else {}
+tr["step:C%d:F%d:taps%d:h%d" % (C, F, taps, h)] = out
+json.dump(tr, open(path, "w"), indent=1)
+print(json.dumps(out, indent=1))
