@@ -346,3 +346,35 @@ def test_fir_p_single_level_with_tail(gpu_lib, block, taps, shared):
     got2 = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
     assert rms(got2 - want) <= RMS_TOL, (plan, rms(got2 - want))
     ch.close()
+
+
+@pytest.mark.parametrize("case", ["all8", "window", "scattered", "latency", "biquad_first"])
+def test_fir_direct_block_io_variants(gpu_lib, case):
+    """Whole aligned blocks on single-level plans are read and written by the fused kernel itself: clusters of four
+    adjacent channels when the selected channels are contiguous (all 8; channels 4..11 of 12), one channel per
+    CTA otherwise (scattered selector); into the compact buffer of fir's latency ring; and after an in-place
+    neighbour in the same chain (in == out)."""
+    from oracle import restate
+    fs, F, taps = 48000, 4096, 20000
+    rng = np.random.default_rng(7)
+    C = 8 if case in ("all8", "latency", "biquad_first") else 12
+    sel = None
+    if case == "window":
+        sel = [4 <= c < 12 for c in range(C)]
+    if case == "scattered":
+        sel = [c in (1, 2, 5, 6, 7, 10, 11, 3) for c in range(C)]
+    n_sel = C if sel is None else sum(sel)
+    h = np.stack([restate.bench_ir(taps, c) for c in range(n_sel)], axis=1)
+    lat = 24576 if case == "latency" else 0
+    x = rng.standard_normal((6 * F + 100, C)) * 0.2
+    ch = gpu_lib.Chain(fs, C)
+    xin = x
+    if case == "biquad_first":
+        coefs = eq_coefs(gpu_lib, fs, 2)
+        ch.add_biquad(coefs)
+        xin = restate.biquad_cascade(x, coefs)
+    ch.add_fir(h, selector=sel, latency=lat, block_hint=F)
+    want = restate.fir_stream(xin, h, selector=sel, latency=lat)
+    got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, x.shape[0], F)])
+    assert rms(got - want) <= RMS_TOL, (case, rms(got - want))
+    ch.close()
