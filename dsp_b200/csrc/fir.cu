@@ -575,7 +575,7 @@ struct MacBatchArgs {
 };
 
 template <int T, bool SHARED_H>
-__global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
+__global__ void __launch_bounds__(256, (T <= 4) ? 3 : 2) k_fir_mac_batch(MacBatchArgs a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = blockIdx.y;
@@ -635,7 +635,24 @@ __global__ void __launch_bounds__(256) k_fir_mac_batch(MacBatchArgs a)
 	}
 }
 
-constexpr int FIR_T_BATCH = 4;
+constexpr int FIR_T_BATCH = 4;   // default batch depth; DSP_B200_FIR_T=6|8 selects the other instantiations
+
+static void launch_mac_batch(int T, bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b)
+{
+	ProfScope prof("fir_mac_batch", st);
+	if (T == 8) {
+		if (shared_h) LAUNCH((k_fir_mac_batch<8, true>), grid, threads, 0, st, b);
+		else LAUNCH((k_fir_mac_batch<8, false>), grid, threads, 0, st, b);
+	}
+	else if (T == 6) {
+		if (shared_h) LAUNCH((k_fir_mac_batch<6, true>), grid, threads, 0, st, b);
+		else LAUNCH((k_fir_mac_batch<6, false>), grid, threads, 0, st, b);
+	}
+	else {
+		if (shared_h) LAUNCH((k_fir_mac_batch<4, true>), grid, threads, 0, st, b);
+		else LAUNCH((k_fir_mac_batch<4, false>), grid, threads, 0, st, b);
+	}
+}
 
 // Bulk form of the whole convolution sum for calls that bring several whole blocks at once (offline rendering,
 // `dsp -b 65536`): Y_i = sum_{p<P} X_{j+i-p} H_p for the nb <= T new blocks i in ONE pass -- every FDL row
@@ -1086,8 +1103,10 @@ struct FirOp : Op {
 				d_Y_side = dev_alloc<double2>((size_t) pf * n_sel * L.B);
 				if (!d_Y_side) return -1;
 				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
-				if (L.P >= 2 * FIR_T_BATCH + pf + 1 && !(nb && nb[0] == '1')) {
-					t_batch = FIR_T_BATCH;
+				int tb = FIR_T_BATCH;
+				if (const char *e = getenv("DSP_B200_FIR_T")) tb = (atoi(e) == 8) ? 8 : (atoi(e) == 6) ? 6 : 4;
+				if (L.P >= 2 * tb + pf + 1 && !(nb && nb[0] == '1')) {
+					t_batch = tb;
 					d_V = dev_alloc<double2>((size_t) 2 * t_batch * n_sel * L.B);
 					if (!d_V) return -1;
 					int lo = 0, hi = 0;
@@ -1253,11 +1272,7 @@ struct FirOp : Op {
 				b.pf = 1;
 				const int threads = (L.B < 256) ? L.B : 256;
 				dim3 grid(L.B / threads, n_sel);
-				{
-					ProfScope prof("fir_mac_batch", bs);
-					if (fc == 1) LAUNCH((k_fir_mac_batch<FIR_T_BATCH, true>), grid, threads, 0, bs, b);
-					else LAUNCH((k_fir_mac_batch<FIR_T_BATCH, false>), grid, threads, 0, bs, b);
-				}
+				launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
 				CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
 			}
 		}
@@ -1302,11 +1317,7 @@ struct FirOp : Op {
 			b.pf = 2;
 			const int threads = (L.B < 256) ? L.B : 256;
 			dim3 grid(L.B / threads, n_sel);
-			{
-				ProfScope prof("fir_mac_batch", bs);
-				if (fc == 1) LAUNCH((k_fir_mac_batch<FIR_T_BATCH, true>), grid, threads, 0, bs, b);
-				else LAUNCH((k_fir_mac_batch<FIR_T_BATCH, false>), grid, threads, 0, bs, b);
-			}
+			launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
 			CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
 		}
 		return 0;
