@@ -378,3 +378,66 @@ def test_fir_direct_block_io_variants(gpu_lib, case):
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, x.shape[0], F)])
     assert rms(got - want) <= RMS_TOL, (case, rms(got - want))
     ch.close()
+
+
+def test_full_size_config2_biquad_cascade(gpu_lib):
+    """BASELINE config 2 at full size: gain -12 dB + 10 eq stages, 256 channels, 48 kHz, 4096-frame blocks; every
+    channel against the restated recurrence (biquad.h:76-92), sweep + per-channel tones as SURVEY 8d prescribes."""
+    from oracle import restate
+    fs, C, F, nblk = 48000, 256, 4096, 3
+    coefs = eq_coefs(gpu_lib, fs, 10)
+    x = restate.sgen_sine(fs, C, nblk * F, 20.0, 20000.0) * 0.5
+    t = np.arange(nblk * F)[:, None] / fs
+    x += 0.25 * np.sin(2 * np.pi * (100.0 + np.arange(C)[None, :]) * t)
+    g = 10.0 ** (-12.0 / 20.0)
+    want = restate.biquad_cascade(x * g, coefs)
+    ch = gpu_lib.Chain(fs, C).add_gain(np.full(C, g)).add_biquad(coefs)
+    got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, nblk * F, F)])
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+    ch.close()
+
+
+def test_full_size_config4_resample(gpu_lib, have_ref):
+    """BASELINE config 4 at full size: 44100 -> 48000, 1024 channels (tensor-core kernel, 8 CTA columns).  Channels
+    c and c + 8 carry the same signal: the first 8 are checked against the oracle, the rest must equal them bit for
+    bit (a channel's result may not depend on the lane / warp / CTA that computes it)."""
+    from oracle import restate
+    fi, fo, C, F, nblk = 44100, 48000, 1024, 4096, 3
+    tt = np.arange(nblk * F)[:, None] / fi
+    base = np.sin(2 * np.pi * (500.0 + 250.0 * np.arange(8)[None, :]) * tt) * 0.5 + restate.sgen_sine(fi, 8, nblk * F, 20.0, 20000.0) * 0.25
+    x = np.tile(base, (1, C // 8))
+    if have_ref:
+        from oracle import ref
+        r = ref.RefChain("resample %d" % fo, fi, 8)
+    else:
+        r = restate.Resampler(fi, fo, 8)
+    ch = gpu_lib.Chain(fi, C).add_resample(fo)
+    for i in range(0, nblk * F, F):
+        want = r.run(base[i:i + F])
+        got = ch.run(x[i:i + F]).copy()
+        assert got.shape == (want.shape[0], C)
+        assert rms(got[:, :8] - want) <= RMS_TOL
+        assert np.array_equal(got, np.tile(got[:, :8], (1, C // 8)))
+    ch.close()
+
+
+def test_full_size_config5_chain_share(gpu_lib, have_ref):
+    """One GPU's share of BASELINE config 5: 8 eq stages + fir_p 65536 taps (shared IR) + resample 44100 -> 48000,
+    256 channels; 4 distinct signals tiled over the channels, checked against the oracle composition."""
+    from oracle import restate
+    fi, fo, C, F, nblk = 44100, 48000, 256, 4096, 4
+    coefs = eq_coefs(gpu_lib, fi, 8)
+    h = restate.bench_ir(65536)
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((nblk * F, 4)) * 0.2
+    x = np.tile(base, (1, C // 4))
+    y = restate.fir_stream(restate.biquad_cascade(base, coefs), h)
+    r = restate.Resampler(fi, fo, 4)
+    ch = gpu_lib.Chain(fi, C).add_biquad(coefs).add_fir(h, block_hint=F).add_resample(fo)
+    for i in range(0, nblk * F, F):
+        want = r.run(y[i:i + F])
+        got = ch.run(x[i:i + F]).copy()
+        assert got.shape == (want.shape[0], C)
+        assert rms(got[:, :4] - want) <= RMS_TOL
+        assert np.array_equal(got, np.tile(got[:, :4], (1, C // 4)))
+    ch.close()
