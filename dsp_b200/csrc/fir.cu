@@ -302,8 +302,11 @@ __device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 h)
 // drops each channel's samples into its owner's transform buffer through distributed shared memory; results
 // travel back the same way.  (One channel per CTA reads 8 of every 32-byte sector it touches: the fused kernel
 // took 43 us that way against 30 us with staged per-channel copies.)
+#ifndef FIR_L0_MAXNREG
+#define FIR_L0_MAXNREG 128
+#endif
 template <int N, int P, bool CL = false>
-__global__ void __launch_bounds__(FftCfg<N>::THREADS, (N == 4096) ? 2 : 1) k_fir_level0(L0Args a)
+__global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? FIR_L0_MAXNREG : 128) k_fir_level0(L0Args a)
 {
 	extern __shared__ double2 smem[];
 	constexpr int T = FftCfg<N>::T, CPB = FftCfg<N>::CPB;
@@ -505,8 +508,11 @@ struct MacArgs {
 	long h_ch_stride;     // P*N or 0 (shared IR)
 };
 
+#ifndef FIR_MAC_MINB
+#define FIR_MAC_MINB 3
+#endif
 template <bool SHARED_H>
-__global__ void __launch_bounds__(256) k_fir_mac(MacArgs a)
+__global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = blockIdx.y;
@@ -575,7 +581,7 @@ struct MacBatchArgs {
 };
 
 template <int T, bool SHARED_H>
-__global__ void __launch_bounds__(256, (T <= 4) ? 3 : 2) k_fir_mac_batch(MacBatchArgs a)
+__global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_batch(MacBatchArgs a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = blockIdx.y;
