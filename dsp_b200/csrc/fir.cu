@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		crank = cluster.block_rank();
 #pragma unroll
 		for (int c = 0; c < 4; ++c) rbuf[c] = cluster.map_shared_rank(buf, c);
+		cluster.sync();   // a CTA's shared memory may only be touched once that CTA is known to be running
 	}
 
 	if (active) {
