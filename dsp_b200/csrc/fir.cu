@@ -8,21 +8,31 @@
 // fir_p.c:290-335) is a CPU latency device; its output is exactly the linear convolution, which is
 // what is kept.
 //
-// B200 formulation.  Per selected channel the stream is kept in a contiguous history ring
-// (k_fir_stash transposes each interleaved block into it).  The filter is cut into LEVELS of
-// doubling partition size, all overlap-add with a frequency-domain delay line (FDL):
-//   level 0: partition B0 = the call's block size (power of two <= 8192), taps [0, 2 B0)  (all taps if
-//            the filter is short), advanced on every block of B0 frames
-//   level l: partition B_l = 2^l B0 <= 8192, taps [B_l, 2 B_l) -- the last level takes all remaining
-//            taps in P_l partitions -- advanced whenever B_l frames have accumulated; a level's result
-//            for its block J is due one block period later (its taps start at B_l), so it is simply
-//            computed when block J completes and added during block J+1 ("pend" buffer)
-// For one level with partition B:  X_j = RFFT_2B([x_j | 0]) -> FDL slot j mod P           (k_fir_fwd)
-//                                  S_j = sum_{p<P} X_{j-p} . H_p   streams FDL + H          (k_fir_mac)
-//                                  s_j = IRFFT_2B(S_j); y_j = s_j[0:B) + carry; carry = s_j[B:2B)  (k_fir_inv)
+// B200 formulation.  Overlap-add with a frequency-domain delay line (FDL) per selected channel; the filter
+// is cut into LEVELS whose partition size doubles from the call's block size B0 up to 4096 (a single level
+// when B0 is already that large; DSP_B200_FIR_LEVEL_CAP moves the cap):
+//   level 0: partition B0 (power of two <= 8192), advanced on every block of B0 frames
+//   level l: partition B_l = 2^l B0, taps [B_l, 2 B_l), advanced whenever B_l frames have accumulated; its
+//            result for block J is due when block J completes and is added during the next period ("pend")
+//   the last level takes all remaining taps in P partitions.
+// For one level with partition B:  X_j = RFFT_2B([x_j | 0]) -> FDL slot j mod R
+//                                  S_j = sum_{p<P} X_{j-p} . H_p
+//                                  s_j = IRFFT_2B(S_j); y_j = s_j[0:B) + carry; carry = s_j[B:2B)
+// Who computes what:
+//   k_fir_level0<B,P>   ONE kernel per level and block: forward transform, spectrum into the FDL, the first
+//                       pf = P partitions of S_j from registers, + Y_j (below), inverse transform, overlap.
+//                       On single-level plans it reads the caller's interleaved block and writes the caller's
+//                       result itself (clusters of four adjacent channels share the rows through DSMEM).
+//   k_fir_mac           Y_j = V_j + sum_{pf<=p<pf+T} X_{j-p} . H_p on a side stream, a block period ahead (the
+//                       blocks it needs were complete pf periods ago): the HBM-streaming kernel
+//   k_fir_mac_batch<T>  V_j = sum_{p>=pf+T} X_{j-p} . H_p for T periods at once (filter rows slide through a
+//                       register window: every FDL and filter row is read once per T outputs)
+//   k_fir_mac_bulk<8>   calls that bring several whole 8192-blocks: all partitions of up to 8 new blocks in
+//                       one pass, with one forward and one inverse launch (k_fir_fwd / k_fir_inv, gridDim.y)
+//   k_fir_stash/unstash interleaved <-> per-channel copies for multi-level plans and ragged calls
 // Spectra are stored "packed": B complex per row, bin 0 = (DC.re, Nyquist.re); rows are 16 B bytes
-// long, 128-byte aligned.  The MAC is the HBM-bound kernel; larger partitions for the late taps cut
-// its bytes per sample (131072 taps, 4096-frame blocks: 1040 B/sample uniform -> 576 B/sample).
+// long, 128-byte aligned.  131072 taps, 4096-frame blocks: 1040 algorithmic bytes per sample for the plain
+// uniform scheme, 508 with the fused kernel + time-batched tail.
 //
 // Calls that are not whole aligned blocks take the general path, exact for ANY frames-per-call
 // pattern: with R_j = sum_{1<=p<P0} X_{j-p} . H_p (completed level-0 blocks only)
