@@ -1002,7 +1002,7 @@ struct FirOp : Op {
 	int t_batch = 0;
 	double2 *d_V = nullptr;
 	cudaStream_t side2 = nullptr;
-	cudaEvent_t ev_batch[2] = { nullptr, nullptr }, ev_main2 = nullptr;
+	cudaEvent_t ev_batch[2] = { nullptr, nullptr };
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
 	// bulk form (single-level plans): up to nb_max whole blocks of one call are transformed, multiplied and
@@ -1040,7 +1040,6 @@ struct FirOp : Op {
 		}
 		for (cudaEvent_t e : ev_batch)
 			if (e) cudaEventDestroy(e);
-		if (ev_main2) cudaEventDestroy(ev_main2);
 		for (cudaEvent_t e : ev_tail)
 			if (e) cudaEventDestroy(e);
 		dev_free(d_V);
@@ -1131,7 +1130,6 @@ struct FirOp : Op {
 					CUDA_TRY(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, lo), return -1);
 					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[0], cudaEventDisableTiming), return -1);
 					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[1], cudaEventDisableTiming), return -1);
-					CUDA_TRY(cudaEventCreateWithFlags(&ev_main2, cudaEventDisableTiming), return -1);
 				}
 			}
 			if (L.B > Bmax) Bmax = L.B;
