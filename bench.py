@@ -17,6 +17,7 @@ the partition-MAC kernel (k_fir_mac) against the measured HBM peak; `cpu_baselin
 reference (oracle/_ref) on this box's host cores over a bounded sample.
 """
 import argparse
+import math
 import json
 import multiprocessing as mp
 import os
@@ -162,20 +163,30 @@ def cpu_reference_run(block, warm, steps=0, seconds=10.0, ch_per_proc=2, procs=N
     try:
         if procs is None:
             cands = sorted(set(max(1, ncpu // d) for d in (4, 2, 1)))
-            best = None
-            for p in cands:
-                rate, _, _, _ = _cpu_trial(ir_path, p, ch_per_proc, block, 2, 0, 2.0)
-                if best is None or rate > best[0]:
-                    best = (rate, p)
-            procs = best[1]
-        rate, blocks, wall, nmax = _cpu_trial(ir_path, procs, ch_per_proc, block, warm, steps, seconds)
+        else:
+            cands = [procs]
+        best = None
+        for p in cands:
+            rate, _, _, _ = _cpu_trial(ir_path, p, ch_per_proc, block, 2, 0, 2.0)
+            if best is None or rate > best[0]:
+                best = (rate, p)
+        procs = best[1]
+        per_step = 1
+        if steps:
+            # fir_p defers most of its arithmetic to worker threads with a two-period deadline (fir_p.c:105-114,
+            # 407): a handful of blocks is over before that work has been done once.  One "step" of this arm is
+            # therefore a sample of `per_step` blocks per process, sized so that the K timed steps cover >= 5 s.
+            blk_rate = best[0] / (procs * ch_per_proc * block)          # blocks per second and process
+            per_step = max(1, int(math.ceil(5.0 * blk_rate / steps)))
+        rate, blocks, wall, nmax = _cpu_trial(ir_path, procs, ch_per_proc, block, warm * per_step, steps * per_step, seconds)
     finally:
         os.remove(ir_path)
         os.rmdir(tmp)
     return {"value": rate / 1e6, "unit": UNIT, "cores": procs, "kind": "reference",
-            "sample": "%d processes (of %d host cores; best of n/4, n/2, n) x %d ch x %d-frame blocks, %d blocks in %.1f s; "
-                      "FFT backend = oracle/fftw3_shim.c (FFTW3 absent)" % (procs, ncpu, ch_per_proc, block, blocks, wall),
-            "ms_per_step": wall / max(1, nmax) * 1e3, "steps_done": nmax, "channels": procs * ch_per_proc}
+            "sample": "%d processes (of %d host cores; best of n/4, n/2, n) x %d ch x %d-frame blocks, %d blocks in %.1f s%s; "
+                      "FFT backend = oracle/fftw3_shim.c (FFTW3 absent)" % (procs, ncpu, ch_per_proc, block, blocks, wall,
+                                                                            (" (1 step = %d blocks per process)" % per_step) if steps else ""),
+            "ms_per_step": wall / max(1, nmax // per_step) * 1e3, "steps_done": nmax // per_step, "channels": procs * ch_per_proc}
 
 
 # ------------------------------------------------------------------------------------------------
