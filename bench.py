@@ -10,11 +10,17 @@ independent streams, no collective on the data path).  One "step" = one block of
     python bench.py --impl reference [...]                         # the reference's CPU path
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line on rank 0.  `value` = device-resident throughput (inputs in HBM, CUDA events
-on the launching stream); `e2e` = the same blocks through the C-ABI host call
-(dspb200_chain_run_host) from pinned host memory, copies inside the timed region; `roofline` =
-the partition-MAC kernel (k_fir_mac) against the measured HBM peak; `cpu_baseline` = the compiled
-reference (oracle/_ref) on this box's host cores over a bounded sample.
+Prints ONE JSON line on rank 0.
+  value         device-resident throughput (inputs in HBM).  The timed region is closed over EVERY stream the
+                chain uses (dspb200_chain_join before the end event), so the look-ahead MAC launches that belong
+                to the timed blocks are inside it.
+  e2e           the same blocks through the C-ABI host call (dspb200_chain_run_host) from pinned host memory,
+                copies inside the timed region.
+  roofline      algorithmic HBM bytes of all kernels of a step / step time, against the measured HBM peak, plus a
+                per-kernel table (each kernel timed alone).
+  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores over a bounded sample.
+  configs       (1 GPU runs) driver-run numbers for BASELINE configs 2-5, the CLI-default 2048-frame block, and
+                `e2e_dropin`: run_effects_chain() of the reference's chain runtime with the GPU effects linked in.
 """
 import argparse
 import math
@@ -38,6 +44,8 @@ CHANNELS_PER_GPU = 256
 TAPS = 131072
 METRIC = "Msamples/s through 256-ch 128k-tap fir_p chain"
 UNIT = "Msamples/s"
+EQ_F = [31.25, 62.5, 125, 250, 500, 1000, 2000, 4000, 8000, 16000]
+EQ_G = [-2, 1.5, -1, 2, -1.5, 1, -2, 1.5, -1, 2]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -65,6 +73,47 @@ def make_irs(taps, channels, first_channel=0):
 def make_block(frames, channels, seed):
     u = park_miller(1000 + seed, frames * channels) / 2147483647.0 - 0.5
     return u.reshape(frames, channels)
+
+
+# ------------------------------------------------------------------------------------------------
+# host placement: a rank's pinned buffers and its copy-issuing thread belong on its GPU's NUMA node
+# ------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Cores this process may really use: the affinity mask, capped by a cgroup CPU quota if there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(math.ceil(float(q) / float(p)))))
+    except Exception:
+        pass
+    return n
+
+
+def bind_to_gpu_numa(device):
+    """sched_setaffinity to the CPUs of the NUMA node the GPU hangs off (first-touch then places the pinned
+    buffers there).  Returns a description for the JSON line, or None when the topology cannot be read."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device)
+        busid = "%04x:%02x:%02x.0" % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % busid).read().strip())
+        if node < 0:
+            return {"pci": busid, "numa_node": node, "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"pci": busid, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"pci": busid, "numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:                                             # topology files missing in this container
+        return {"bound": False, "why": str(e)[:80]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -121,11 +170,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU legs: the compiled reference on host cores (the only place oracle/ is executed here)
 # ------------------------------------------------------------------------------------------------
+CPU_FLAVOURS = [("O2", "libdspref.so", "-O2"), ("Os", "libdspref_Os.so", "-Os (the reference's own level, GNUmakefile:57)"),
+                ("O3", "libdspref_O3.so", "-O3 -march=x86-64-v3 (stand-in for -march=native: built off-box)")]
+
+
 def _cpu_worker(args):
-    ir_path, ch, block, warm, steps, seconds = args
+    lib_path, ir_path, ch, block, warm, steps, seconds = args
     sys.path.insert(0, ROOT)
     from oracle import ref          # checker / baseline only
-    c = ref.RefChain("fir_p -t pcm -e double -c %d -r %d %s" % (ch, FS, ir_path), FS, ch)
+    c = ref.RefChain("fir_p -t pcm -e double -c %d -r %d %s" % (ch, FS, ir_path), FS, ch, lib_path=lib_path)
     c.run_inplace(block, refill=True)
     for _ in range(warm):
         c.run_inplace(block)
@@ -139,54 +192,229 @@ def _cpu_worker(args):
     return n, dt
 
 
-def _cpu_trial(ir_path, procs, ch_per_proc, block, warm, steps, seconds):
+def _cpu_trial(lib_path, ir_path, procs, ch_per_proc, block, warm, steps, seconds):
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(ir_path, ch_per_proc, block, warm, steps, seconds)] * procs)
+        res = pool.map(_cpu_worker, [(lib_path, ir_path, ch_per_proc, block, warm, steps, seconds)] * procs)
     # every process ran concurrently; job throughput = sum of the per-process rates
     rate = sum(n * block * ch_per_proc / dt for n, dt in res)
     return rate, sum(n for n, _ in res), max(dt for _, dt in res), max(n for n, _ in res)
 
 
-def cpu_reference_run(block, warm, steps=0, seconds=10.0, ch_per_proc=2, procs=None):
-    """The reference on the host cores: P processes, each a reference fir_p chain of `ch_per_proc` channels with
-    its own 131072-tap IRs (channels are independent, so this is how the reference would use the box; each process
-    also runs fir_p's own worker threads, fir_p.c:105-114).  P is tuned over {n/4, n/2, n} cores first and the best
-    is kept, so the baseline is not handicapped by oversubscription."""
+def cpu_reference_suite(block, sample_s=5.0, runs=3, one_proc_s=3.0, ch_per_proc=2):
+    """The reference on the host cores: for every build flavour (i) ONE process (fir_p's own <= 3
+    worker threads included) and (ii) P processes, each a reference fir_p chain of `ch_per_proc` channels with its own
+    131072-tap IRs (channels are independent: this is how the reference would use the box).  P is picked once, from
+    2-second trials over {n/4, n/2, n} usable cores; the P-process figure is the median of `runs` samples of
+    `sample_s` seconds, with the spread.  fir_p defers most of its arithmetic to worker threads with a two-period
+    deadline (fir_p.c:105-114): samples are seconds long so that work is inside them."""
     from oracle import ref
     if not ref.available():
         return None
-    ncpu = os.cpu_count() or 1
+    ncpu = usable_cores()
+    ref_dir = os.path.dirname(ref.LIB_PATH)
+    flavours = [(k, os.path.join(ref_dir, f), d) for k, f, d in CPU_FLAVOURS if os.path.exists(os.path.join(ref_dir, f))]
     tmp = tempfile.mkdtemp(prefix="dspb200_bench_")
     ir_path = os.path.join(tmp, "ir.f64")
     make_irs(TAPS, ch_per_proc).astype("<f8").tofile(ir_path)
+    out = {"cores_usable": ncpu, "cores_os": os.cpu_count(), "flavours": {}}
     try:
-        if procs is None:
-            cands = sorted(set(max(1, ncpu // d) for d in (4, 2, 1)))
-        else:
-            cands = [procs]
-        best = None
+        cands = sorted(set(max(1, ncpu // d) for d in (4, 2, 1)))
+        trials = {}
         for p in cands:
-            rate, _, _, _ = _cpu_trial(ir_path, p, ch_per_proc, block, 2, 0, 2.0)
-            if best is None or rate > best[0]:
-                best = (rate, p)
-        procs = best[1]
-        per_step = 1
-        if steps:
-            # fir_p defers most of its arithmetic to worker threads with a two-period deadline (fir_p.c:105-114,
-            # 407): a handful of blocks is over before that work has been done once.  One "step" of this arm is
-            # therefore a sample of `per_step` blocks per process, sized so that the K timed steps cover >= 5 s.
-            blk_rate = best[0] / (procs * ch_per_proc * block)          # blocks per second and process
-            per_step = max(1, int(math.ceil(5.0 * blk_rate / steps)))
-        rate, blocks, wall, nmax = _cpu_trial(ir_path, procs, ch_per_proc, block, warm * per_step, steps * per_step, seconds)
+            trials[p] = _cpu_trial(flavours[0][1], ir_path, p, ch_per_proc, block, 2, 0, 2.0)[0] / 1e6
+        procs = max(trials, key=trials.get)
+        out["process_count_trials_Msps"] = {str(k): round(v, 2) for k, v in trials.items()}
+        for key, path, desc in flavours:
+            one = _cpu_trial(path, ir_path, 1, ch_per_proc, block, 2, 0, one_proc_s)[0] / 1e6
+            samples = sorted(_cpu_trial(path, ir_path, procs, ch_per_proc, block, 2, 0, sample_s)[0] / 1e6 for _ in range(runs))
+            out["flavours"][key] = {"build": desc, "one_process_Msps": one, "n_process_Msps_median": samples[len(samples) // 2],
+                                    "n_process_Msps_min": samples[0], "n_process_Msps_max": samples[-1], "processes": procs}
     finally:
         os.remove(ir_path)
         os.rmdir(tmp)
-    return {"value": rate / 1e6, "unit": UNIT, "cores": procs, "kind": "reference",
-            "sample": "%d processes (of %d host cores; best of n/4, n/2, n) x %d ch x %d-frame blocks, %d blocks in %.1f s%s; "
-                      "FFT backend = oracle/fftw3_shim.c (FFTW3 absent)" % (procs, ncpu, ch_per_proc, block, blocks, wall,
-                                                                            (" (1 step = %d blocks per process)" % per_step) if steps else ""),
-            "ms_per_step": wall / max(1, nmax // per_step) * 1e3, "steps_done": nmax // per_step, "channels": procs * ch_per_proc}
+    best = max(out["flavours"], key=lambda k: out["flavours"][k]["n_process_Msps_median"])
+    b = out["flavours"][best]
+    out.update({"value": b["n_process_Msps_median"], "unit": UNIT, "cores": procs, "kind": "reference", "flavour": best,
+                "spread": [b["n_process_Msps_min"], b["n_process_Msps_max"]],
+                "sample": "fastest build (%s) of the unmodified reference: median of %d samples x %.0f s, %d processes (of %d usable cores; best of n/4, n/2, n) "
+                          "x %d ch x %d-frame blocks, own 131072-tap IRs; FFT backend = oracle/fftw3_shim.c (FFTW3 absent: pessimistic for the CPU)"
+                          % (best, runs, sample_s, procs, ncpu, ch_per_proc, block),
+                "channels": procs * ch_per_proc})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident timing of one chain: CUDA events on the launching stream, region closed over all streams
+# ------------------------------------------------------------------------------------------------
+def time_device(chain, d_in, d_out_ptr, frames, steps, warm, stream, barrier=None):
+    """-> (milliseconds for `steps` calls after `warm` untimed ones, kernels launched inside the timed region).
+    d_in: list of device tensors (rotating)."""
+    import torch
+    import dsp_b200
+    n = len(d_in)
+    for i in range(warm):
+        chain.run_device(0, frames, d_in[i % n].data_ptr(), d_out_ptr, stream)
+    chain.join(0, stream)
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = dsp_b200.kernel_launches()
+    e0.record()
+    for i in range(steps):
+        chain.run_device(0, frames, d_in[i % n].data_ptr(), d_out_ptr, stream)
+    chain.join(0, stream)            # side-stream work of the timed blocks is inside the region
+    e1.record()
+    launches = dsp_b200.kernel_launches() - l0
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1), launches
+
+
+def fir_bytes_model(plan, C, F, h):
+    """Algorithmic HBM bytes per input sample of every kernel of a K2 step from the operator's plan."""
+    lv = plan["levels"]
+    lvl = lv[-1]
+    pf = int(plan.get("tail_pf", 0))
+    tb = int(plan.get("t_batch", 0))
+    pipe = int(plan.get("pipe", 0))
+    ppf = int(plan.get("pipe_pf", 0))
+    parts = {}
+    P = lvl["P"]
+    if pipe:
+        # persistent pipeline kernel: in 8, spectrum to the FDL 16, (ppf-1) FDL rows, ppf filter rows, V, carry r/w, out
+        parts["fir_pipe"] = 8 + 16 + 16.0 * (ppf - 1) + 16.0 * ppf * h + (16 if tb else 0) + 8 + 8 + 8
+        if tb:
+            parts["fir_mac_batch"] = 16.0 * ((P - 2 - 1) + (P - 2 - tb) * h + tb) / tb
+        return sum(parts.values()), parts
+    n_lv = len(lv)
+    if pf == 0:
+        mac = 16.0 * (P * (1 + h) + 1)
+        batch = 0.0
+    elif tb:
+        mac = 16.0 * (tb * (1 + h) + 2)
+        batch = 16.0 * ((P - pf - 1) + (P - pf - tb) * h + tb) / tb
+    else:
+        mac = 16.0 * ((P - pf) * (1 + h) + 1)
+        batch = 0.0
+    parts = {"stash_unstash": 0.0, "fir_level0": 0.0, "fir_fwd_inv": 0.0, "fir_mac": mac, "fir_mac_batch": batch}
+    direct = n_lv == 1 and (pf != 0 or P <= 2)
+    if not direct:
+        parts["stash_unstash"] = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)
+    for i, L in enumerate(lv):
+        in_kernel = min(L["P"], 2 if i == 0 else 1)
+        has_init = pf and i == n_lv - 1
+        if pf == 0 and i == 0 and L["P"] > 2:
+            parts["fir_fwd_inv"] += (8 + 16) + (16 + 8 + 8 + 8)
+            continue
+        parts["fir_level0"] += 8 + 16 + 16 * (in_kernel - 1) + 16 * in_kernel * h + (16 if has_init else 0) + 8 + 8 + 8
+    return sum(parts.values()), parts
+
+
+def eq_coefs(dsp, fs, n):
+    return np.array([dsp.biquad_design(13, fs, EQ_F[i], 1.4, EQ_G[i]) for i in range(n)])
+
+
+def measure_configs(dsp, torch, irs, peak, local_rank, dropin_steps):
+    """Driver-run numbers for the other BASELINE configs (device-resident, 200 blocks each after 5 warm-ups) and for
+    the drop-in call path.  Every entry: Msamples/s in, ms per block, and the roofline fraction of its bound."""
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    steps, warm = 200, 5
+
+    def entry(name, chain, C, F, fs, bytes_per_sample, extra=None, out_frames=None, note=None):
+        d_in = [torch.from_numpy(make_block(F, C, 500 + i)).cuda() for i in range(4)]
+        of = out_frames or F
+        d_out = torch.empty((of + 8, C), dtype=torch.float64, device="cuda")
+        ms, _ = time_device(chain, d_in, d_out.data_ptr(), F, steps, warm, stream)
+        rate = C * F * steps / (ms * 1e-3)
+        e = {"workload": name, "value": rate / 1e6, "unit": UNIT, "ms_per_block": ms / steps, "blocks": steps, "block_frames": F,
+             "channels": C, "fs": fs,
+             "roofline": {"bound": "hbm", "algorithmic_bytes_per_sample": bytes_per_sample, "achieved": bytes_per_sample * rate / 1e9,
+                          "peak": peak, "unit": "GB/s", "frac": bytes_per_sample * rate / 1e9 / peak}}
+        if extra:
+            e.update(extra)
+        if note:
+            e["note"] = note
+        chain.close()
+        del d_in, d_out
+        return e
+
+    # C2: 10-stage eq cascade, 256 ch, 4096-frame blocks (K1: one read + one write of the block)
+    C, F = 256, 4096
+    ch = dsp.Chain(FS, C, devices=[local_rank]).add_biquad(eq_coefs(dsp, FS, 10))
+    out["C2"] = entry("10 x eq cascade, 256 ch, 48 kHz, 4096-frame blocks", ch, C, F, FS, 16.0,
+                      note="K1 fused cascade; FP64-issue/latency-bound, HBM bound is 16 B/sample")
+    # C3: fir_p 131072 taps, 64 channels
+    C = 64
+    ch = dsp.Chain(FS, C, devices=[local_rank]).add_fir(irs[:, :C], block_hint=F)
+    plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
+    bps, _ = fir_bytes_model(plan, C, F, 1)
+    out["C3"] = entry("fir_p 131072 taps x 64 ch, per-channel IR, 4096-frame blocks", ch, C, F, FS, bps, extra={"plan": plan})
+    # H at the CLI's default block (dsp.h:38)
+    C, F2 = 256, 2048
+    ch = dsp.Chain(FS, C, devices=[local_rank]).add_fir(irs[:, :C], block_hint=F2)
+    plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
+    bps, _ = fir_bytes_model(plan, C, F2, 1)
+    out["H_2048"] = entry("fir_p 131072 taps x 256 ch, per-channel IR, 2048-frame blocks (CLI default)", ch, C, F2, FS, bps, extra={"plan": plan})
+    # C4: resample 44100 -> 48000, 1024 ch
+    C, fs4 = 1024, 44100
+    ch = dsp.Chain(fs4, C, devices=[local_rank]).add_resample(48000)
+    of = ch.max_out_frames(F)
+    rp = dsp.resample_params(fs4, 48000)
+    flop_per_in = 2.0 * rp["taps_per_phase"] * rp["n"] / rp["d"]
+    e = entry("resample 44100 -> 48000, 1024 ch, 4096-frame blocks", ch, C, F, fs4, 8.0 * (1 + rp["n"] / rp["d"]), out_frames=of)
+    e["fp64"] = {"flop_per_input_sample": flop_per_in, "achieved_tflops": flop_per_in * e["value"] * 1e6 / 1e12,
+                 "fp64_tflops_measured": 37.1, "fp64_peak_source": "scripts/micro/dmma_probe.cu on this pool's B200 (round 1)",
+                 "frac_of_fp64_peak": flop_per_in * e["value"] * 1e6 / 1e12 / 37.1}
+    e["note"] = "polyphase form as north_star words it: FP64-tensor-core (DMMA) bound, not HBM bound"
+    out["C4"] = e
+    # C5 share: 8 eq + fir_p 65536 (shared IR) + resample, 256 ch at 44100
+    C = 256
+    h5 = make_ir(65536, 0)
+    ch = dsp.Chain(fs4, C, devices=[local_rank]).add_biquad(eq_coefs(dsp, fs4, 8)).add_fir(h5, block_hint=F).add_resample(48000)
+    plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
+    bps, _ = fir_bytes_model(plan, C, F, 0)
+    of = ch.max_out_frames(F)
+    out["C5_share"] = entry("8 x eq + fir_p 65536 taps (shared IR) + resample 44100 -> 48000, 256 ch (one GPU's share of config 5)", ch, C, F,
+                            fs4, 16.0 + bps + 8.0 * (1 + 160.0 / 147.0), out_frames=of, extra={"plan": plan})
+
+    # e2e_dropin: run_effects_chain() of the reference chain runtime with the shim's GPU effects (shim/frontend.c)
+    try:
+        from dsp_b200 import frontend
+        if frontend.available():
+            C, F = 256, 4096
+            tmp = tempfile.mkdtemp(prefix="dspb200_dropin_")
+            ir_path = os.path.join(tmp, "ir.f64")
+            np.ascontiguousarray(irs[:, :C], dtype="<f8").tofile(ir_path)
+            pool = np.stack([make_block(F, C, 700 + i) for i in range(4)])
+            dd = {}
+            for label, pin in (("pageable", None), ("pinned", "1")):
+                if pin:
+                    os.environ["DSP_B200_PIN"] = pin
+                else:
+                    os.environ.pop("DSP_B200_PIN", None)
+                fc = frontend.DropinChain("fir_p -t pcm -e double -c %d -r %d %s" % (C, FS, ir_path), FS, C)
+                sec, f, chk = fc.time(pool, 5, dropin_steps)
+                dd[label] = {"value": C * F * dropin_steps / sec / 1e6, "unit": UNIT, "ms_per_block": sec / dropin_steps * 1e3,
+                             "blocks": dropin_steps, "effects": fc.effect_names(), "checksum": chk,
+                             "buffers": "the frontend's calloc block buffers" + (", page-locked once by the shim (DSP_B200_PIN=1)" if pin else ", pageable")}
+                fc.close()
+            os.environ.pop("DSP_B200_PIN", None)
+            os.remove(ir_path)
+            os.rmdir(tmp)
+            dd["api"] = "run_effects_chain() (reference effects_chain.c, unmodified) -> shim effect->run() -> dspb200_chain_run_host, in place; clock_gettime around each call"
+            dd["workload"] = "fir_p 131072 taps x 256 ch, 4096-frame blocks (the headline through the drop-in)"
+            out["e2e_dropin"] = dd
+        else:
+            out["e2e_dropin"] = {"unavailable": "shim/_build/libdsp_b200_frontend.so not built (needs the reference sources at build time)"}
+    except Exception as ex:                                            # a failing side measurement must not sink the headline
+        out["e2e_dropin"] = {"error": str(ex)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,15 +422,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block", type=int, default=4096)
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU, help="channels per GPU")
     ap.add_argument("--taps", type=int, default=TAPS)
     ap.add_argument("--shared-ir", action="store_true", help="one IR for all channels (-c 1) instead of one per channel")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel (serialised) timing pass")
     ap.add_argument("--e2e-slabs", type=int, default=4)
     a = ap.parse_args()
 
@@ -228,16 +457,20 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_run(a.block, warm, steps=steps)
+        r = cpu_reference_suite(a.block)
         if r is None:
             emit({"impl": "reference", "unavailable": "oracle/_ref/libdspref.so not built (needs /root/reference at build time)"})
             return 0
+        ms_step = r["channels"] * a.block / (r["value"] * 1e6) * 1e3        # one step = one block of every process's channels
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-                "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "flavour", "spread", "flavours", "cores_usable",
+                                                   "cores_os", "process_count_trials_Msps")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "gpu_launches": 0,
+                "note": "time-bounded samples (the reference's fir_p defers work to threads: a fixed handful of blocks reads too fast); "
+                        "--steps/--warmup are echoed, the samples are 3 x 5 s per build flavour"}
         emit(line)
         return 0
 
@@ -247,6 +480,7 @@ def main():
     if dsp_b200.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank)      # before any pinned allocation
     job = Job()                      # NCCL process group when WORLD_SIZE > 1: barrier + scalar reductions only
     barrier, reduce_max, reduce_sum = job.barrier, job.reduce_max, job.reduce_sum
 
@@ -260,71 +494,17 @@ def main():
     d_blocks = [torch.from_numpy(b).cuda() for b in blocks]
     d_out = torch.empty((F, C), dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    for i in range(warm):
-        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    dsp_b200.profile_read("fir_mac")
-    dsp_b200.profile_enable(True)
-    launches0 = dsp_b200.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
-    e1.record()
-    barrier()
-    launches = dsp_b200.kernel_launches() - launches0
-    dsp_b200.profile_enable(False)
-    ms = reduce_max(e0.elapsed_time(e1))
+    ms, launches = time_device(chain, d_blocks, d_out.data_ptr(), F, steps, warm, stream, barrier=barrier)
+    ms = reduce_max(ms)
     total_samples = float(world) * C * F * steps
     value = total_samples / (ms * 1e-3) / 1e6
     checksum = float(d_out.abs().sum().item())
 
-    # roofline of the dominant kernel = the MAC of the LAST partition level (it carries almost all taps).
-    # Algorithmic bytes of one launch: per selected channel and bin, P FDL rows + (per-channel IR)
-    # P filter rows read and 1 row written, 16 B each.
     plan = [op for op in chain.describe() if op.get("op") == "fir"][0]
-    lvl = plan["levels"][-1]
     h = 0 if a.shared_ir else 1
-    # tail_pf = partitions of the last level summed inside its fused FFT kernel (0: no tail machinery, the plain
-    # three-kernel path; 1: an upper level carries the tail; 2: single level, the kernel sums partitions 0 and 1)
-    pf = int(plan.get("tail_pf", 0))
-    tb = int(plan.get("t_batch", 0))
-    batch_bytes = 0.0
-    if pf == 0:
-        mac_parts = lvl["P"]
-        mac_bytes = C * lvl["B"] * 16.0 * (mac_parts * (1 + h) + 1)
-    elif tb:
-        # time-batched tail: every period k_fir_mac streams T partitions plus the batched spectrum (read) and writes Y;
-        # every T periods k_fir_mac_batch streams the other FDL rows and filter rows once for T outputs
-        mac_parts = tb
-        mac_bytes = C * lvl["B"] * 16.0 * (tb * (1 + h) + 2)
-        batch_bytes = C * lvl["B"] * 16.0 * ((lvl["P"] - pf - 1) + (lvl["P"] - pf - tb) * h + tb)
-    else:
-        mac_parts = lvl["P"] - pf
-        mac_bytes = C * lvl["B"] * 16.0 * (mac_parts * (1 + h) + 1)
-    tail_per_sample = (mac_bytes + (batch_bytes / tb if tb else 0.0)) / (C * lvl["B"])
-    step_bytes = tail_per_sample * C * F + sum(C * L["B"] * 16.0 * (min(L["P"], 2 if i == 0 else 1) * (1 + h)) * (F / L["B"])
-                                               for i, L in enumerate(plan["levels"]))
-
-    def step_budget():
-        """algorithmic HBM bytes per input sample of every kernel of a step: total and per kernel"""
-        n_lv = len(plan["levels"])
-        parts = {"stash_unstash": 0.0, "fir_level0": 0.0, "fir_fwd_inv": 0.0, "fir_mac": mac_bytes / (C * lvl["B"]),
-                 "fir_mac_batch": (batch_bytes / tb if tb else 0.0) / (C * lvl["B"])}
-        direct = n_lv == 1 and pf != 0 or (n_lv == 1 and lvl["P"] <= 2)     # fused kernel reads/writes the interleaved block itself
-        if not direct:
-            parts["stash_unstash"] = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)   # stash (read + write), unstash (y + pending sums + write)
-        for i, L in enumerate(plan["levels"]):
-            in_kernel = min(L["P"], 2 if i == 0 else 1)
-            has_init = pf and i == n_lv - 1
-            if pf == 0 and i == 0 and L["P"] > 2:
-                parts["fir_fwd_inv"] += (8 + 16) + (16 + 8 + 8 + 8)           # separate forward and inverse transforms
-                continue
-            parts["fir_level0"] += 8 + 16 + 16 * (in_kernel - 1) + 16 * in_kernel * h + (16 if has_init else 0) + 8 + 8 + 8
-        return sum(parts.values()), parts
-
+    per_sample, parts = fir_bytes_model(plan, C, F, h)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -334,58 +514,51 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "step:C%d:F%d:taps%d:h%d" % (C, F, a.taps, h)
+        key = "step:C%d:F%d:taps%d:h%d:pipe%d" % (C, F, a.taps, h, int(plan.get("pipe", 0)))
         traffic = tr.get(key, {}).get("dram_bytes_per_step")
     except Exception:
         pass
-    roofline = None
-    per_sample, parts = step_budget()
     step_s = ms / steps * 1e-3
-    in_loop = {}
-    for nme in ("fir_level0", "fir_mac", "fir_mac_batch", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk"):
-        t_ms, n_l = dsp_b200.profile_read(nme)
-        if n_l:
-            in_loop[nme] = (t_ms / n_l * 1e3, n_l / float(steps))
-    if step_s > 0:
-        ach = per_sample * C * F / step_s / 1e9
-        roofline = {"bound": "hbm",
-                    "kernel": "one step = every kernel of the chain for one block (%s), on three concurrent streams" % ", ".join("k_" + k for k in in_loop),
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                    "algorithmic_bytes_per_step": per_sample * C * F, "algorithmic_bytes_per_sample": per_sample,
-                    "bytes_per_sample_by_kernel": parts, "avg_step_us": step_s * 1e6,
-                    "partition_levels": plan["levels"], "t_batch": tb, "tail_pf": pf,
-                    "note": "achieved = algorithmic bytes of all kernels of a step / measured step time (CUDA events over the timed loop). "
-                            "The kernels of a step run concurrently on three streams and time-slice the GPU, so a single kernel's "
-                            "event-bracketed duration inside the loop is not its own speed; `kernels` gives each kernel timed alone "
-                            "(side streams folded into one) next to its in-loop figure."}
-    # isolated kernel durations: a short extra pass with the side streams folded into the caller's stream
-    iso = {}
-    dsp_b200.debug_serialize(True)
-    for i in range(2 * 8):
-        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
-    torch.cuda.synchronize()
-    names = ("fir_mac", "fir_mac_batch", "fir_level0", "fir_inv", "fir_fwd", "fir_mac_bulk")
-    for nme in names:
-        dsp_b200.profile_read(nme)
-    dsp_b200.profile_enable(True)
-    for i in range(8 * 8):
-        chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
-    torch.cuda.synchronize()
-    dsp_b200.profile_enable(False)
-    dsp_b200.debug_serialize(False)
-    for nme in names:
-        t_ms, n_l = dsp_b200.profile_read(nme)
-        if n_l:
-            iso[nme] = t_ms / n_l * 1e3
-    if roofline is not None:
-        alg = {"fir_level0": parts["fir_level0"] * C * plan["levels"][0]["B"] if len(plan["levels"]) == 1 else None,
-               "fir_mac": mac_bytes, "fir_mac_batch": batch_bytes if tb else None}
+    ach = per_sample * C * F / step_s / 1e9
+    knames = ("fir_pipe", "fir_level0", "fir_mac", "fir_mac_batch", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk")
+    roofline = {"bound": "hbm",
+                "kernel": "one step = every kernel of the chain for one block, the look-ahead MACs on their own streams",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_step": per_sample * C * F, "algorithmic_bytes_per_sample": per_sample,
+                "bytes_per_sample_by_kernel": parts, "avg_step_us": step_s * 1e6,
+                "plan": plan,
+                "note": "achieved = algorithmic bytes of all kernels of a step / measured step time; the timed region ends after "
+                        "dspb200_chain_join (every stream of the chain).  `kernels`: each kernel timed alone (side streams folded "
+                        "into the caller's stream, profiling events on), outside the headline region."}
+    # per-kernel durations: a separate pass with the side streams folded into the caller's stream and event brackets on
+    if not a.no_kernels:
+        iso = {}
+        dsp_b200.debug_serialize(True)
+        for i in range(16):
+            chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        for nme in knames:
+            dsp_b200.profile_read(nme)
+        dsp_b200.profile_enable(True)
+        n_iso = 64
+        for i in range(n_iso):
+            chain.run_device(0, F, d_blocks[i % n_pool].data_ptr(), d_out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        dsp_b200.profile_enable(False)
+        dsp_b200.debug_serialize(False)
         kern = {}
-        for nme in sorted(set(list(iso) + list(in_loop))):
-            e = {"launches_per_step": in_loop.get(nme, (None, 0.0))[1], "in_step_event_us": in_loop.get(nme, (None, 0.0))[0],
-                 "alone_us": iso.get(nme), "algorithmic_bytes_per_launch": alg.get(nme)}
-            if e["alone_us"] and e["algorithmic_bytes_per_launch"]:
+        nB = C * plan["levels"][-1]["B"]
+        for nme in knames:
+            t_ms, n_l = dsp_b200.profile_read(nme)
+            if not n_l:
+                continue
+            per_launch = parts.get(nme)
+            e = {"launches_per_step": n_l / float(n_iso), "alone_us": t_ms / n_l * 1e3}
+            if per_launch:
+                # bytes_per_sample_by_kernel is per input sample; a launch of the batch kernel covers t_batch block periods
+                mult = plan.get("t_batch", 1) if nme == "fir_mac_batch" else 1
+                e["algorithmic_bytes_per_launch"] = per_launch * nB * mult
                 e["alone_GBs"] = e["algorithmic_bytes_per_launch"] / (e["alone_us"] * 1e-6) / 1e9
                 e["alone_frac"] = e["alone_GBs"] / peak
             kern["k_" + nme] = e
@@ -413,7 +586,7 @@ def main():
         dt = reduce_max(dt)
         e2e = {"value": total_samples / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": F * C * 8, "d2h_bytes_per_step": F * C * 8,
                "ms_per_step": dt / steps * 1e3, "api": "dspb200_chain_run_host, pinned host buffers (inputs write-combined), %d channel slabs" % a.e2e_slabs,
-               "checksum": float(np.abs(pout.array).sum())}
+               "numa": numa, "checksum": float(np.abs(pout.array).sum())}
         # the same blocks through submit/wait: up to `depth` blocks in flight, each with its own output buffer
         depth = 3
         pouts = [dsp_b200.PinnedArray((F, C)) for _ in range(depth + 1)]
@@ -432,6 +605,7 @@ def main():
                 acc += float(pouts[(i - depth) % (depth + 1)].array[0, 0])     # the block is on the host now
         for t in tickets[-depth:]:
             ch2.wait(t)
+        torch.cuda.synchronize()
         dtp = time.perf_counter() - t0
         barrier()
         dtp = reduce_max(dtp)
@@ -444,18 +618,26 @@ def main():
     clocks = sampler.stop()          # sampled across both timed loops (device-resident and host-call)
     launches_total = int(reduce_sum(float(launches)))
 
+    configs = None
+    if rank == 0 and world == 1 and not a.no_configs:
+        try:
+            configs = measure_configs(dsp_b200, torch, irs if not a.shared_ir else make_irs(a.taps, C), peak, local_rank, dropin_steps=100)
+        except Exception as ex:
+            configs = {"error": str(ex)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        r = cpu_reference_run(F, 2, seconds=a.cpu_seconds)
+        r = cpu_reference_suite(F)
         if r:
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "flavour", "spread", "flavours", "cores_usable", "cores_os",
+                                     "process_count_trials_Msps")}
 
     if rank == 0:
-        config["l2"] = "per-step working set %.2f GB of FDL+filter spectra streamed from HBM (> 126 MB L2); %d rotating input blocks" % (step_bytes / 1e9, n_pool)
+        config["l2"] = "per-step working set %.2f GB of FDL+filter spectra streamed from HBM (> 126 MB L2); %d rotating input blocks" % (per_sample * C * F / 1e9, n_pool)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-                "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum}
+                "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "configs": configs, "checksum": checksum}
         emit(line)
     job.close()
     return 0

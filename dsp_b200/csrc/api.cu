@@ -33,6 +33,22 @@ void set_error(const char *fmt, ...)
 
 const char *get_error() { return tls_error; }
 
+static thread_local bool tls_launch_failed = false;
+
+void note_launch_error(const char *kernel, cudaError_t err)
+{
+	set_error("launch of %s failed: %s", kernel, cudaGetErrorString(err));
+	tls_launch_failed = true;
+	cudaGetLastError();   // clear the non-sticky error so that later calls report their own
+}
+
+bool take_launch_error()
+{
+	const bool f = tls_launch_failed;
+	tls_launch_failed = false;
+	return f;
+}
+
 // per-kernel timing: pairs of events recorded around launches while profiling is enabled
 std::atomic<int> g_profile_on{0};
 namespace {
@@ -245,6 +261,7 @@ struct Shard {
 			}
 			if (f > 0) {
 				f = op->run(f, cur, dst, st);
+				if (take_launch_error()) return -1;   // message already set by LAUNCH
 				if (f < 0) return -1;
 			}
 			cur = dst;
@@ -265,7 +282,8 @@ struct dspb200_chain {
 	std::vector<std::unique_ptr<Shard>> shards;
 	std::vector<std::pair<void *, size_t>> registered;    // host ranges pinned by us
 	bool pin_host = false;
-	unsigned long long ticket = 0;   // blocks submitted so far (dspb200_chain_submit_host)
+	unsigned long long ticket = 0;   // blocks submitted so far (dspb200_chain_submit_host); bumped only by a complete submission
+	unsigned long long waited = 0;   // highest ticket known to be complete
 
 	~dspb200_chain()
 	{
@@ -579,7 +597,12 @@ long dspb200_chain_submit_host(dspb200_chain *c, long frames, const double *in, 
 	maybe_pin(c, in, (size_t) frames * C * sizeof(double));
 	if (out != in) maybe_pin(c, out, (size_t) ((max_out > frames) ? max_out : frames) * C * sizeof(double));
 	long result = -1;
-	const unsigned long long t = ++c->ticket;
+	const unsigned long long t = c->ticket + 1;   // becomes current only when every shard has been enqueued
+	if (ticket && t > c->waited + Shard::DONE_RING) {
+		// the completion markers are a ring of DONE_RING: the oldest outstanding block is waited for here
+		// rather than letting its marker be overwritten
+		if (dspb200_chain_wait(c, t - Shard::DONE_RING)) return -1;
+	}
 	FOR_EACH_SHARD(c, s) {
 		CUDA_TRY(cudaSetDevice(s->device), return -1);
 		if (s->ensure_cap(frames)) return -1;
@@ -597,6 +620,7 @@ long dspb200_chain_submit_host(dspb200_chain *c, long frames, const double *in, 
 		}
 		result = f;
 	}
+	c->ticket = t;
 	if (ticket) *ticket = t;
 	return result;
 }
@@ -612,6 +636,7 @@ int dspb200_chain_wait(dspb200_chain *c, unsigned long long ticket)
 		if (ev) CUDA_TRY(cudaEventSynchronize(ev), return -1);
 		else CUDA_TRY(cudaStreamSynchronize(s->stream), return -1);
 	}
+	if (ticket > c->waited) c->waited = ticket;
 	return 0;
 }
 
@@ -625,6 +650,7 @@ long dspb200_chain_run_host(dspb200_chain *c, long frames, const double *in, dou
 		cudaSetDevice(s->device);
 		CUDA_TRY(cudaStreamSynchronize(s->stream), return -1);
 	}
+	c->waited = c->ticket;
 	return result;
 }
 
@@ -637,6 +663,16 @@ long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const do
 	if (s->ensure_cap(frames)) return -1;
 	cudaStream_t st = (cudaStream_t) stream;   // NULL = the legacy default stream, as everywhere in CUDA
 	return s->run_ops(0, frames, d_in, d_out, false, st, false);
+}
+
+int dspb200_chain_join(dspb200_chain *c, int shard, void *stream)
+{
+	if (!c || shard < 0 || shard >= (int) c->shards.size()) return -1;
+	Shard *s = c->shards[shard].get();
+	CUDA_TRY(cudaSetDevice(s->device), return -1);
+	for (auto &op : s->ops)
+		if (op->join((cudaStream_t) stream)) return -1;
+	return 0;
 }
 
 long dspb200_chain_drain_host(dspb200_chain *c, long frames, double *out)
@@ -691,6 +727,7 @@ int dspb200_chain_sync(dspb200_chain *c)
 		cudaSetDevice(s->device);
 		CUDA_TRY(cudaStreamSynchronize(s->stream), return -1);
 	}
+	c->waited = c->ticket;
 	return 0;
 }
 

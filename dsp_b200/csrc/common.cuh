@@ -29,10 +29,17 @@ const char *get_error();
 	} while (0)
 
 // ---- launch accounting (dspb200_kernel_launches()) ----------------------------------------
+// A rejected launch configuration (grid too large, shared memory the device refuses, ...) is a
+// non-sticky error that no later CUDA_TRY would see: LAUNCH records it (message + a per-thread flag)
+// and the chain's operator loop turns the flag into a failed call (take_launch_error()).
 extern std::atomic<long long> g_kernel_launches;
+void note_launch_error(const char *kernel, cudaError_t err);
+bool take_launch_error();   // true once after a failed launch on this thread
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                     \
 	do {                                                                                   \
 		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                        \
+		const cudaError_t lerr__ = cudaPeekAtLastError();                                  \
+		if (lerr__ != cudaSuccess) ::dspb200::note_launch_error(#kernel, lerr__);          \
 		::dspb200::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);              \
 	} while (0)
 
@@ -98,6 +105,13 @@ struct Op {
 	{
 		(void) frames; (void) zeros; (void) out; (void) st;
 		return -1;
+	}
+	// Operators that keep work on streams of their own (K2's look-ahead MACs): make `st` wait for everything
+	// enqueued there so far.  dspb200_chain_join(): closes a timed region over ALL of the chain's device work.
+	virtual int join(cudaStream_t st)
+	{
+		(void) st;
+		return 0;
 	}
 };
 

@@ -140,8 +140,18 @@ __device__ __forceinline__ void dft<16>(double2 (&v)[16])
 		}
 }
 
+// Who synchronises between the phases of a pass: the whole CTA (default), or -- in warp-specialised kernels
+// where only some warps transform -- a named barrier over the transforming threads.
+struct CtaSync {
+	static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+template <int ID, int COUNT>
+struct NamedSync {
+	static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+};
+
 // One radix-R Stockham pass over s[0..N) (sub-transform length so far: Ns); ptw = this pass's table.
-template <int N, int R>
+template <int N, int R, class Sync = CtaSync>
 __device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__ ptw, int t, int Ns)
 {
 	constexpr int T = FftCfg<N>::T;
@@ -154,7 +164,7 @@ __device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__
 #pragma unroll
 		for (int r = 0; r < R; ++r) v[b][r] = s[spad(j + r * BF)];
 	}
-	__syncthreads();
+	Sync::sync();
 #pragma unroll
 	for (int b = 0; b < PT; ++b) {
 		const int j = t + b * T;
@@ -177,27 +187,28 @@ __device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__
 #pragma unroll
 		for (int r = 0; r < R; ++r) s[spad(j0 + r * Ns)] = v[b][r];
 	}
-	__syncthreads();
+	Sync::sync();
 }
 
-template <int N, int PASS, int NS, int OFF>
+template <int N, int PASS, int NS, int OFF, class Sync>
 struct FftPasses {
 	static __device__ __forceinline__ void run(double2 *s, const double2 *__restrict__ ptw, int t)
 	{
 		constexpr int R = fft_radix(N, PASS);
 		if constexpr (R != 0) {
-			fft_pass<N, R>(s, ptw + OFF, t, NS);
-			FftPasses<N, PASS + 1, NS * R, OFF + ((NS > 1) ? 4 * NS : 0)>::run(s, ptw, t);
+			fft_pass<N, R, Sync>(s, ptw + OFF, t, NS);
+			FftPasses<N, PASS + 1, NS * R, OFF + ((NS > 1) ? 4 * NS : 0), Sync>::run(s, ptw, t);
 		}
 	}
 };
 
 // Forward complex DFT (exp(-2 pi i nk/N)) of s[0..N), natural order in and out.
-// All FftCfg<N>::THREADS threads of the CTA must call it; t = thread index within the FFT.
-template <int N>
+// All threads that Sync synchronises (default: the FftCfg<N>::THREADS threads of the CTA) must call it;
+// t = thread index within the FFT.
+template <int N, class Sync = CtaSync>
 __device__ __forceinline__ void fft_forward_smem(double2 *s, const double2 *__restrict__ ptw, int t)
 {
-	FftPasses<N, 0, 1, 0>::run(s, ptw, t);
+	FftPasses<N, 0, 1, 0, Sync>::run(s, ptw, t);
 }
 
 }  // namespace dspb200

@@ -42,6 +42,7 @@
 // ever look at completed blocks.  All paths share {history, FDLs, carries, block counters}.
 #include "common.cuh"
 #include "fft.cuh"
+#include "fir_pipe.cuh"
 #include "ops.h"
 #include <cooperative_groups.h>
 
@@ -884,6 +885,42 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 	return 0;
 }
 
+// the persistent pipeline (fir_pipe.cuh): one CTA per SM, channels strided over the grid
+template <int N>
+static int launch_pipe_n(const PipeArgs &a, cudaStream_t st)
+{
+	static std::atomic<int> configured[64];
+	static std::atomic<int> sm_count[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!configured[dev & 63].load()) {
+		CUDA_TRY(cudaFuncSetAttribute(k_fir_pipe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PipeCfg<N>::SMEM), return -1);
+		int sms = 0;
+		CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), return -1);
+		sm_count[dev & 63].store(sms);
+		configured[dev & 63].store(1);
+	}
+	if (a.n_ch <= 0) return 0;
+	int grid = sm_count[dev & 63].load();
+	if (const char *e = getenv("DSP_B200_FIR_PIPE_GRID")) grid = atoi(e);
+	if (grid > a.n_ch) grid = a.n_ch;
+	if (grid < 1) grid = 1;
+	ProfScope prof("fir_pipe", st);
+	LAUNCH(k_fir_pipe<N>, grid, PipeCfg<N>::THREADS, PipeCfg<N>::SMEM, st, a);
+	return 0;
+}
+
+static int launch_pipe(int N, const PipeArgs &a, cudaStream_t st)
+{
+	switch (N) {
+	case 2048: return launch_pipe_n<2048>(a, st);
+	case 4096: return launch_pipe_n<4096>(a, st);
+	default: set_error("pipeline kernel: unsupported block size %d", N); return -1;
+	}
+}
+
+static bool pipe_size_ok(int N) { return N == 2048 || N == 4096; }
+
 #define DISPATCH_N(N_, FN, ...)                      \
 	switch (N_) {                                    \
 	case 64: return FN<64>(__VA_ARGS__);             \
@@ -993,6 +1030,11 @@ struct FirOp : Op {
 	double2 *d_Y = nullptr;              // [n_sel][max B]
 	double2 *d_Y_side = nullptr;         // [n_sel][B last]: the tail spectrum of the next block period (side stream); two of them when level 0 has the tail
 	int tail_pf = 0;                     // 0: no tail; 1: tail on an upper level; 2: tail on level 0 (single-level plan, fused kernel sums p = 0, 1)
+	// single-level plans of 2048/4096-frame blocks: whole aligned blocks go through the persistent pipeline
+	// (fir_pipe.cuh), which sums partitions 0 .. pipe_pf-1 (+ the batched V) itself -- no per-block k_fir_mac
+	bool use_pipe = false;
+	int pipe_pf = 0;
+	int pipe_evict_first = getenv("DSP_B200_FIR_PIPE_EVICT") ? atoi(getenv("DSP_B200_FIR_PIPE_EVICT")) : 1;
 	cudaEvent_t ev_tail[2] = { nullptr, nullptr };
 	double *d_ring = nullptr, *d_ltmp = nullptr;
 	// side stream: the upper levels' partition-0 kernels and the last level's tail MAC overlap the main stream
@@ -1003,6 +1045,7 @@ struct FirOp : Op {
 	double2 *d_V = nullptr;
 	cudaStream_t side2 = nullptr;
 	cudaEvent_t ev_batch[2] = { nullptr, nullptr };
+	cudaEvent_t ev_join[2] = { nullptr, nullptr };
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
 	// bulk form (single-level plans): up to nb_max whole blocks of one call are transformed, multiplied and
@@ -1024,7 +1067,8 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"tail_pf\":%d,\"bulk\":%d}", t_batch, tail_pf, nb_max);
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}", t_batch, tail_pf, nb_max,
+		         use_pipe ? 1 : 0, pipe_pf);
 		return buf;
 	}
 
@@ -1041,6 +1085,8 @@ struct FirOp : Op {
 		for (cudaEvent_t e : ev_batch)
 			if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : ev_tail)
+			if (e) cudaEventDestroy(e);
+		for (cudaEvent_t e : ev_join)
 			if (e) cudaEventDestroy(e);
 		dev_free(d_V);
 		if (ev_main) cudaEventDestroy(ev_main);
@@ -1116,8 +1162,12 @@ struct FirOp : Op {
 			if (has_tail) {
 				L.tail = true;
 				tail_pf = pf;
-				d_Y_side = dev_alloc<double2>((size_t) pf * n_sel * L.B);
-				if (!d_Y_side) return -1;
+				const char *pe = getenv("DSP_B200_FIR_PIPE");
+				use_pipe = (l == 0) && direct_io && pipe_size_ok(L.B) && !(pe && pe[0] == '0');
+				if (!use_pipe) {
+					d_Y_side = dev_alloc<double2>((size_t) pf * n_sel * L.B);
+					if (!d_Y_side) return -1;
+				}
 				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
 				int tb = FIR_T_BATCH;
 				if (const char *e = getenv("DSP_B200_FIR_T")) tb = (atoi(e) == 8) ? 8 : (atoi(e) == 6) ? 6 : 4;
@@ -1131,6 +1181,7 @@ struct FirOp : Op {
 					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[0], cudaEventDisableTiming), return -1);
 					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[1], cudaEventDisableTiming), return -1);
 				}
+				if (use_pipe) pipe_pf = (t_batch > 0) ? t_batch + 2 : L.P;
 			}
 			if (L.B > Bmax) Bmax = L.B;
 		}
@@ -1177,6 +1228,18 @@ struct FirOp : Op {
 		h_taps.clear();
 		h_taps.shrink_to_fit();
 		planned = true;
+		return 0;
+	}
+
+	int join(cudaStream_t st) override
+	{
+		cudaStream_t ss[2] = { side, side2 };
+		for (int i = 0; i < 2; ++i) {
+			if (!ss[i]) continue;
+			if (!ev_join[i]) CUDA_TRY(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming), return -1);
+			CUDA_TRY(cudaEventRecord(ev_join[i], ss[i]), return -1);
+			CUDA_TRY(cudaStreamWaitEvent(st, ev_join[i], 0), return -1);
+		}
 		return 0;
 	}
 
@@ -1309,6 +1372,17 @@ struct FirOp : Op {
 		const bool on_main = serial || tail_main > 0;
 		cudaStream_t ts = on_main ? st : side, bs = serial ? st : side2;
 		const long q = L.blk - 1, j = q + 2;
+		if (use_pipe) {
+			// the pipeline kernel sums partitions 0 .. pipe_pf-1 itself: only the batched V is produced ahead of time
+			if (t_batch > 0 && q % t_batch == 0) {
+				if (!serial) {
+					CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
+					CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
+				}
+				if (launch_batch0(L, q, bs)) return -1;
+			}
+			return 0;
+		}
 		double2 *Y = d_Y_side + (size_t) (j & 1) * n_sel * L.B;
 		if (!serial) {
 			CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
@@ -1326,15 +1400,32 @@ struct FirOp : Op {
 		CUDA_TRY(cudaEventRecord(ev_tail[j & 1], ts), return -1);
 		if (t_batch > 0 && q % t_batch == 0) {
 			if (!serial) CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
-			MacBatchArgs b = {};
-			b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
-			b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
-			b.pf = 2;
-			const int threads = (L.B < 256) ? L.B : 256;
-			dim3 grid(L.B / threads, n_sel);
-			launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
-			CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
+			if (launch_batch0(L, q, bs)) return -1;
 		}
+		return 0;
+	}
+
+	// V_j = sum_{p >= 2+T} X_{j-p} H_p for the T periods j = q+3 .. q+2+T, from the blocks up to q (level 0 of a single-level plan)
+	int launch_batch0(FirLevel &L, long q, cudaStream_t bs)
+	{
+		MacBatchArgs b = {};
+		b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
+		b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+		b.pf = 2;
+		const int threads = (L.B < 256) ? L.B : 256;
+		dim3 grid(L.B / threads, n_sel);
+		launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
+		CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
+		return 0;
+	}
+
+	// The main stream may only go on with block `blk` of a single-level tail plan once the batch that produced V_blk
+	// is complete: the pipeline kernel reads V_blk, and every path overwrites FDL row blk % P, which that batch
+	// (launched after block T*floor((blk-3)/T)) still reads until then.
+	int wait_batch_for(long blk, cudaStream_t st)
+	{
+		if (t_batch > 0 && tail_pf == 2 && blk >= 3 && !g_fir_serialize.load(std::memory_order_relaxed))
+			CUDA_TRY(cudaStreamWaitEvent(st, ev_batch[((blk - 3) / t_batch) & 1], 0), return -1);
 		return 0;
 	}
 
@@ -1420,11 +1511,11 @@ struct FirOp : Op {
 	long run(long frames, const double *in, double *out, cudaStream_t st) override
 	{
 		if (frames <= 0) return 0;
-		if (!planned && plan(frames, st)) return -1;
 		const long C = channels;
 		if (in != out && n_sel < C)
 			CUDA_TRY(cudaMemcpyAsync(out, in, (size_t) frames * C * sizeof(double), cudaMemcpyDeviceToDevice, st), return -1);
-		if (n_sel == 0) return frames;
+		if (n_sel == 0) return frames;   // a slab the selector leaves empty: pass-through, nothing to plan (no taps were kept for it)
+		if (!planned && plan(frames, st)) return -1;
 
 		// where the convolution result goes: straight to `out`, or to a compact temp when a latency ring follows
 		double *dst = out;
@@ -1468,7 +1559,26 @@ struct FirOp : Op {
 			}
 			if (pos == 0 && seg == B0) {
 				// fast path: one whole aligned block
-				if (L0.P <= 2 || tail_pf == 2) {
+				if (use_pipe && direct) {
+					if (wait_batch_for(L0.blk, st)) return -1;
+					PipeArgs f = {};
+					f.xin = src; f.xin_stride = C; f.xin_map = d_ch_map;
+					f.yout = d; f.yout_stride = dstride; f.yout_map = dmap;
+					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.R * B0; f.fdl_rows = L0.R; f.slot = (int) (L0.blk % L0.R);
+					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
+					f.pf = pipe_pf;
+					f.V = (t_batch > 0 && L0.blk >= 3) ? d_V + (size_t) (L0.blk % (2 * t_batch)) * n_sel * B0 : nullptr;
+					f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
+					f.evict_first = pipe_evict_first;
+					if (launch_pipe(B0, f, st)) return -1;
+					++L0.blk;
+				}
+				else if (use_pipe) {
+					// a whole block that cannot use the direct form (never happens today: direct_io is a plan-time switch)
+					if (wait_batch_for(L0.blk, st)) return -1;
+					if (level_block(L0, d_ytmp, B0, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
+				}
+				else if (L0.P <= 2 || tail_pf == 2) {
 					L0Args f = {};
 					f.in = d_hist + blk_off; f.in_ch_stride = hist_len;
 					if (direct) {
@@ -1505,6 +1615,7 @@ struct FirOp : Op {
 				       d, dstride, dmap, B0, pos, seg);
 				if (pos + seg == B0) {
 					// block complete: X into the FDL, carry = IRFFT(S)[B:2B) (its first half has been emitted already)
+					if (wait_batch_for(L0.blk, st)) return -1;
 					if (level_block(L0, nullptr, 0, INV_UPDATE_CARRY, st)) return -1;
 					pre_valid = false;
 				}

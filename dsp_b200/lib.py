@@ -45,6 +45,7 @@ SIGNATURES = {
     "dspb200_chain_max_out_frames": (C.c_long, [C.c_void_p, C.c_long]),
     "dspb200_chain_run_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]),
     "dspb200_chain_run_device": (C.c_long, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dspb200_chain_join": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "dspb200_chain_drain_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p]),
     "dspb200_chain_reset": (None, [C.c_void_p]),
     "dspb200_chain_sync": (C.c_int, [C.c_void_p]),
@@ -241,6 +242,10 @@ class Chain:
     def run_device(self, shard, frames, d_in, d_out, stream=None):
         """Mode D: raw device pointers (ints), asynchronous on `stream` (cudaStream_t as int)."""
         return _check(lib().dspb200_chain_run_device(self.h, int(shard), int(frames), d_in, d_out, stream), "run_device")
+
+    def join(self, shard, stream=None):
+        """Make `stream` wait for everything the shard's operators have enqueued on streams of their own."""
+        _check(lib().dspb200_chain_join(self.h, int(shard), stream), "join")
 
     def drain(self, frames):
         """One drain2 poll (resample.c:163-188); None when dry."""

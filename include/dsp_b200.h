@@ -121,6 +121,12 @@ int  dspb200_chain_wait(dspb200_chain *c, unsigned long long ticket);
 long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const double *d_in,
                               double *d_out, void *stream);
 
+/* Mode D timing aid: operators may keep look-ahead work on streams of their own (K2's tail MACs run one to
+ * several block periods ahead of the block kernel).  Makes `stream` wait for everything shard `shard`'s operators
+ * have enqueued so far, so that an event recorded on `stream` afterwards closes over ALL device work of the
+ * calls made until now.  Not needed for correctness of later calls. */
+int  dspb200_chain_join(dspb200_chain *c, int shard, void *stream);
+
 /* resample_effect_drain2() semantics (resample.c:163-188) for the whole chain: push zeros
  * until every rate-changing operator is dry.  Returns frames written (0..max_frames*ratio),
  * or -1 when nothing is left. */
