@@ -19,6 +19,22 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
+def build_variant(name, defines):
+    """A measurement variant of the library (compile-time knobs), dsp_b200/variants/libdspb200_<name>.so; select it
+    at run time with DSP_B200_LIB=<path>."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, "libdspb200_%s.so" % name)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo"] + ARCH + ["-D" + d for d in defines] + srcs + ["-o", out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc failed building variant " + name)
+    return out
+
+
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

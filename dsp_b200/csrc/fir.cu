@@ -1035,6 +1035,8 @@ struct FirOp : Op {
 	bool use_pipe = false;
 	int pipe_pf = 0;
 	int pipe_evict_first = getenv("DSP_B200_FIR_PIPE_EVICT") ? atoi(getenv("DSP_B200_FIR_PIPE_EVICT")) : 1;
+	int pipe_fake_io = getenv("DSP_B200_FIR_PIPE_FAKEIO") ? atoi(getenv("DSP_B200_FIR_PIPE_FAKEIO")) : 0;   // measurement only
+	int batch_threads = getenv("DSP_B200_FIR_BATCH_THREADS") ? atoi(getenv("DSP_B200_FIR_BATCH_THREADS")) : 256;
 	cudaEvent_t ev_tail[2] = { nullptr, nullptr };
 	double *d_ring = nullptr, *d_ltmp = nullptr;
 	// side stream: the upper levels' partition-0 kernels and the last level's tail MAC overlap the main stream
@@ -1412,7 +1414,8 @@ struct FirOp : Op {
 		b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
 		b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 		b.pf = 2;
-		const int threads = (L.B < 256) ? L.B : 256;
+		int threads = (batch_threads == 128 || batch_threads == 64) ? batch_threads : 256;
+		if (L.B < threads) threads = L.B;
 		dim3 grid(L.B / threads, n_sel);
 		launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
 		CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
@@ -1570,6 +1573,7 @@ struct FirOp : Op {
 					f.V = (t_batch > 0 && L0.blk >= 3) ? d_V + (size_t) (L0.blk % (2 * t_batch)) * n_sel * B0 : nullptr;
 					f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
 					f.evict_first = pipe_evict_first;
+					f.fake_io = (pipe_fake_io && C == n_sel && dstride == C) ? 1 : 0;
 					if (launch_pipe(B0, f, st)) return -1;
 					++L0.blk;
 				}

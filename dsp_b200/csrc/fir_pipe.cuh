@@ -58,6 +58,7 @@ struct PipeArgs {
 	const double2 *tw, *ptw;
 	int n_ch;
 	int evict_first;         // streaming operands are read once per block: keep them from displacing the rest of L2
+	int fake_io;             // MEASUREMENT ONLY (DSP_B200_FIR_PIPE_FAKEIO): contiguous block I/O (wrong results) to time the kernel without the strided accesses
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) -------------------------------------------
@@ -128,8 +129,13 @@ __device__ __forceinline__ void pipe_prefetch_rows(const void *p, long bytes, in
 	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
+// Register cap: 416 threads x 104 registers leave room for one 256-thread CTA of the batched MAC kernel on the same
+// SM, so that the HBM stream of the look-ahead MAC fills the time this kernel's transform team spends on latency.
+#ifndef FIR_PIPE_MAXNREG
+#define FIR_PIPE_MAXNREG 104
+#endif
 template <int N>
-__global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1) k_fir_pipe(PipeArgs a)
+__global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 {
 	using Cfg = PipeCfg<N>;
 	constexpr int T = Cfg::TF, CHUNK = Cfg::CHUNK, NS = Cfg::NS, PER = Cfg::PER, TM = Cfg::TM;
@@ -168,12 +174,13 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1) k_fir_pipe(PipeArgs a)
 			double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
 			{
 				// frames 2n, 2n+1 of this channel (the CTAs next door read the rest of each sector at about the same time)
-				const double *xc = a.xin + (a.xin_map ? a.xin_map[s] : s);
+				const double *xc = a.fake_io ? a.xin + (long) s * N : a.xin + (a.xin_map ? a.xin_map[s] : s);
+				const long xs = a.fake_io ? 1 : a.xin_stride;
 				double2 v[8];
 #pragma unroll
 				for (int i = 0; i < 8; ++i) {
 					const long n2 = 2L * (t + i * T);
-					v[i] = make_double2(xc[n2 * a.xin_stride], xc[(n2 + 1) * a.xin_stride]);   // plain loads: the call may be in place
+					v[i] = make_double2(xc[n2 * xs], xc[(n2 + 1) * xs]);   // plain loads: the call may be in place
 				}
 				// what the later phases read with plain loads: on its way to L2 while the first transform runs
 				pipe_prefetch_rows(H0, (long) N * sizeof(double2), t, T);
@@ -241,7 +248,8 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1) k_fir_pipe(PipeArgs a)
 			// (3) overlap-add, result into the caller's block
 			{
 				const double scale = 1.0 / N;
-				double *yc = a.yout + (a.yout_map ? a.yout_map[s] : s);
+				double *yc = a.fake_io ? a.yout + (long) s * N : a.yout + (a.yout_map ? a.yout_map[s] : s);
+				const long ys = a.fake_io ? 1 : a.yout_stride;
 				double2 c[8];
 #pragma unroll
 				for (int i = 0; i < 8; ++i) c[i] = carry[t + i * T];
@@ -249,8 +257,8 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1) k_fir_pipe(PipeArgs a)
 				for (int i = 0; i < 8; ++i) {
 					const int n = t + i * T;
 					const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
-					yc[2L * n * a.yout_stride] = fma(lo.x, scale, c[i].x);
-					yc[(2L * n + 1) * a.yout_stride] = fma(-lo.y, scale, c[i].y);
+					yc[2L * n * ys] = fma(lo.x, scale, c[i].x);
+					yc[(2L * n + 1) * ys] = fma(-lo.y, scale, c[i].y);
 					carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 				}
 			}

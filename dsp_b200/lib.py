@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdspb200.so")
+LIB_PATH = os.environ.get("DSP_B200_LIB") or os.path.join(_HERE, "libdspb200.so")   # DSP_B200_LIB: a measurement variant (build.build_variant)
 
 _lib = None
 

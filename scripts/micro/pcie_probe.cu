@@ -114,6 +114,38 @@ int main()
 			k_push<<<grid, 256, 0, s[1]>>>((double2 *) dout, mh_out, F, C / 2, C / 2);
 			CK(cudaStreamSynchronize(s[0])); CK(cudaStreamSynchronize(s[1])); }, 2.0 * bytes);
 	}
+	// one synchronous block in channel slabs: how should the copies of one call be ordered / carried?
+	for (int slabs : { 2, 4, 8 }) {
+		const size_t w = C / slabs * 8, pitch = C * 8;
+		const int w2 = (int) (w / 16), pitch2 = (int) (pitch / 16);
+		char name[128];
+		snprintf(name, sizeof(name), "breadth-first 2-D: all H2D, then D2H per slab stream, %d slabs", slabs);
+		run(name, [&] {
+			for (int k = 0; k < slabs; ++k) CK(cudaMemcpy2DAsync((char *) din + k * w * F, w, (char *) hin + k * w, pitch, w, F, cudaMemcpyHostToDevice, s[k]));
+			for (int k = 0; k < slabs; ++k) CK(cudaMemcpy2DAsync((char *) hout + k * w, pitch, (char *) din + k * w * F, w, w, F, cudaMemcpyDeviceToHost, s[k]));
+			for (int k = 0; k < slabs; ++k) CK(cudaStreamSynchronize(s[k])); }, 2.0 * bytes);
+		snprintf(name, sizeof(name), "CE H2D slab k -> push kernel slab k (SM stores to host), %d slabs", slabs);
+		run(name, [&] {
+			for (int k = 0; k < slabs; ++k) {
+				CK(cudaMemcpy2DAsync((char *) din + k * w * F, w, (char *) hin + k * w, pitch, w, F, cudaMemcpyHostToDevice, s[k]));
+				k_push<<<148, 256, 0, s[k]>>>((double2 *) ((char *) din + k * w * F), mh_out + k * w2, F, w2, pitch2);
+			}
+			for (int k = 0; k < slabs; ++k) CK(cudaStreamSynchronize(s[k])); }, 2.0 * bytes);
+		snprintf(name, sizeof(name), "pull kernel slab k (SM loads from host) -> CE D2H slab k, %d slabs", slabs);
+		run(name, [&] {
+			for (int k = 0; k < slabs; ++k) {
+				k_pull<<<148, 256, 0, s[k]>>>(mh_in + k * w2, (double2 *) ((char *) din + k * w * F), F, w2, pitch2);
+				CK(cudaMemcpy2DAsync((char *) hout + k * w, pitch, (char *) din + k * w * F, w, w, F, cudaMemcpyDeviceToHost, s[k]));
+			}
+			for (int k = 0; k < slabs; ++k) CK(cudaStreamSynchronize(s[k])); }, 2.0 * bytes);
+		snprintf(name, sizeof(name), "pull kernel slab k -> push kernel slab k (no copy engine), %d slabs", slabs);
+		run(name, [&] {
+			for (int k = 0; k < slabs; ++k) {
+				k_pull<<<148, 256, 0, s[k]>>>(mh_in + k * w2, (double2 *) ((char *) din + k * w * F), F, w2, pitch2);
+				k_push<<<148, 256, 0, s[k]>>>((double2 *) ((char *) din + k * w * F), mh_out + k * w2, F, w2, pitch2);
+			}
+			for (int k = 0; k < slabs; ++k) CK(cudaStreamSynchronize(s[k])); }, 2.0 * bytes);
+	}
 	run("copy-engine H2D + kernel push together", [&] {
 		CK(cudaMemcpyAsync(din, hin, bytes, cudaMemcpyHostToDevice, s[0]));
 		k_push<<<148, 256, 0, s[1]>>>((double2 *) dout, mh_out, F, C / 2, C / 2);

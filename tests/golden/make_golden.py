@@ -47,6 +47,13 @@ def main():
     save("fir", "fir -t pcm -e double -c 1 -r 48000 ir700.f64", 48000, 3, 512, x)
     save("fir_direct", "fir coefs:0.5,0.25,-0.125,0.0625,0.03", 48000, 3, 100, x)
     save("hilbert", "hilbert -p 255", 48000, 3, 333, x)
+    # -a alignment (fir_util.c:187-205 -> channel_offsets -> the chain's align pass, effects_chain.c:744-864): the
+    # filtered channels ask for a negative delay (peak index / offset from the end / centre tap), the chain turns the
+    # difference into `align` effects on the OTHER channels.  Drop-in tier only (the align pass is reference code).
+    save("fir_p_align", ":0,2 fir_p -a -t pcm -e double -c 1 -r 48000 ir700.f64", 48000, 3, 256, x)
+    save("fir_align_end", ":1 fir -a-100S -t pcm -e double -c 1 -r 48000 ir700.f64", 48000, 3, 512, x)
+    save("hilbert_c", ":0 hilbert -c 255", 48000, 3, 333, x)
+    save("hilbert_pc", ":0,1 hilbert -p -c 255 :2 eq 1k 1.0 3", 48000, 3, 333, x)
     # resample both ways, ragged blocks, drain included
     x = ref.sgen("sine:freq=1k+3000S", 44100, 2, 3000) * 0.8
     x[:, 1] = rng.standard_normal(3000) * 0.3

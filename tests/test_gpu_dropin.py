@@ -21,7 +21,10 @@ CLI_REF = os.path.join(ROOT, "oracle", "_ref", "dsp_ref")
 RMS_TOL = 1e-10
 
 NAMES = ["gain", "biquad", "fir_p", "fir_p_2ch", "fir", "fir_direct", "hilbert", "resample_up", "resample_down",
-         "resample_2x", "chain"]
+         "resample_2x", "chain",
+         # -a / -c alignment: fir_get_offset -> ref -> channel_offsets -> the reference's align pass (effects_chain.c:744-864)
+         "fir_p_align", "fir_align_end", "hilbert_c", "hilbert_pc"]
+LADSPA = os.path.join(HERE, "dropin", "_build", "ladspa_dsp_b200.so")
 
 
 def load(name):
@@ -47,6 +50,16 @@ def test_dropin_golden(dropin, name):
     assert y.shape == g["y"].shape
     assert rms(y - g["y"]) <= RMS_TOL, rms(y - g["y"])
     c.close()
+
+
+def test_dropin_alignment_effects_are_the_references(dropin):
+    """With -a / -c the GPU effect reports (latency, -ref) through channel_offsets and the reference's own alignment
+    pass appends its `align` effect: same effect list as the pure reference recorded in the golden file."""
+    for name in ("fir_p_align", "fir_align_end", "hilbert_c", "hilbert_pc"):
+        g = load(name)
+        c = dropin.RefChain(str(g["chain"]), int(g["fs"]), int(g["channels"]), dir=GOLDEN, lib_path=DROPIN)
+        assert c.effect_names() == [str(e) for e in g["effects"]], (name, c.effect_names(), list(g["effects"]))
+        c.close()
 
 
 def test_dropin_merge_fuses_gpu_effects(dropin):
@@ -109,3 +122,143 @@ def test_dropin_cli(dropin, tmp_path, have_ref):
         outs.append(np.fromfile(out, dtype="<f8").reshape(-1, 4))
     assert outs[0].shape == outs[1].shape and outs[0].shape[0] > 30000
     assert rms(outs[0] - outs[1]) <= RMS_TOL, rms(outs[0] - outs[1])
+
+
+def test_watch_reloads_gpu_chain_on_its_worker_thread(dropin, tmp_path):
+    """The reference's `watch` effect (watch.c:60-123) rebuilds the watched chain on ITS worker thread -- GPU effect
+    init (device allocations, filter transforms, the library's process-global tables) and, after the crossfade,
+    destroy -- while the caller's thread is inside run() of the old chain; during the crossfade both chains run on the
+    same input.  Before the first reload the output must equal the plain chain exactly; through three reloads
+    (init on the worker thread, crossfade of two GPU chains, destroy of the old one) every block must come back
+    whole and finite."""
+    import threading
+    import time
+    fs, C, F = 48000, 4, 1024
+    ir = os.path.join(GOLDEN, "ir700.f64")
+    chain_a = "eq 1k 1.0 3 fir_p -t pcm -e double -c 1 -r 48000 %s" % ir
+    chain_b = "fir_p -t pcm -e double -c 1 -r 48000 %s eq 300 0.7 -2 hilbert -p 127" % ir
+    path = str(tmp_path / "watched.txt")
+    with open(path, "w") as f:
+        f.write(chain_a + "\n")
+    w = dropin.RefChain("watch %s" % path, fs, C, lib_path=DROPIN)
+    plain = dropin.RefChain(chain_a, fs, C, lib_path=DROPIN)
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal((F, C)) * 0.2
+    assert np.array_equal(w.run(x0), plain.run(x0))
+    plain.close()
+    stop = threading.Event()
+
+    def rewriter():
+        for i in range(3):
+            time.sleep(0.7)
+            with open(path, "w") as f:
+                f.write((chain_b if i % 2 == 0 else chain_a) + "\n")
+        stop.set()
+    t = threading.Thread(target=rewriter)
+    t.start()
+    n = 0
+    t_end = None
+    while True:
+        y = w.run(rng.standard_normal((F, C)) * 0.2)
+        assert y.shape == (F, C) and np.all(np.isfinite(y)) and np.max(np.abs(y)) < 10.0
+        n += 1
+        if stop.is_set() and t_end is None:
+            t_end = time.time() + 1.8        # one more poll interval + the crossfade
+        if t_end is not None and time.time() > t_end:
+            break
+    t.join()
+    assert n > 100
+    w.close()
+
+
+def test_c_abi_is_thread_safe_across_chains(gpu_lib):
+    """One thread keeps calling run_host() on a chain while another builds, plans, runs and destroys other chains
+    (different FFT sizes: the twiddle tables and the profiling map are process-global).  The first thread's output
+    must be bit-identical to a single-threaded run."""
+    import threading
+    from oracle import restate
+    fs, C, F = 48000, 6, 2048
+    rng = np.random.default_rng(8)
+    h = np.stack([restate.bench_ir(9000, c) for c in range(C)], axis=1)
+    xs = [rng.standard_normal((F, C)) * 0.2 for _ in range(60)]
+    ref_chain = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
+    want = [ref_chain.run(x).copy() for x in xs]
+    ref_chain.close()
+    errors = []
+    done = threading.Event()
+
+    def churn():
+        k = 0
+        try:
+            while not done.is_set():
+                taps = [300, 1500, 5000, 20000][k % 4]
+                blk = [64, 256, 1024, 4096][(k // 2) % 4]
+                c = gpu_lib.Chain(fs, 3).add_biquad(np.array([gpu_lib.biquad_design(13, fs, 500.0, 1.0, 2.0)])).add_fir(restate.bench_ir(taps), block_hint=blk)
+                c.run(np.ones((blk, 3)) * 0.1)
+                c.run(np.ones((blk + 7, 3)) * 0.1)
+                c.close()
+                k += 1
+        except Exception as e:          # pragma: no cover
+            errors.append(e)
+    t = threading.Thread(target=churn)
+    t.start()
+    ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
+    got = [ch.run(x).copy() for x in xs]
+    done.set()
+    t.join()
+    ch.close()
+    assert not errors, errors
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+
+
+def test_ladspa_frontend_runs_gpu_chain(dropin, have_ref, tmp_path):
+    """The reference's LADSPA frontend (ladspa_dsp.c, unmodified, -DLADSPA_FRONTEND -DSYMMETRIC_IO) linked against the
+    shim objects: load the plugin as a LADSPA host would (ladspa_descriptor -> instantiate -> connect_port -> run),
+    float32 ports, against the pure reference chain fed the same float32 samples."""
+    import ctypes as C
+    if not os.path.exists(LADSPA):
+        pytest.fail("tests/dropin/_build/ladspa_dsp_b200.so missing")
+    chain = "gain -3 eq 200 1.0 3 :0 hilbert -p 255 : fir_p -t pcm -e double -c 1 -r 48000 %s" % os.path.join(GOLDEN, "ir700.f64")
+    cfg = tmp_path / "ladspa_cfg"
+    cfg.mkdir()
+    (cfg / "config").write_text("input_channels=2\noutput_channels=2\n[effects_chain]\n" + chain + "\n")
+    os.environ["LADSPA_DSP_CONFIG_PATH"] = str(cfg)
+
+    class Desc(C.Structure):
+        pass
+    HANDLE = C.c_void_p
+    Desc._fields_ = [("UniqueID", C.c_ulong), ("Label", C.c_char_p), ("Properties", C.c_int), ("Name", C.c_char_p), ("Maker", C.c_char_p),
+                     ("Copyright", C.c_char_p), ("PortCount", C.c_ulong), ("PortDescriptors", C.POINTER(C.c_int)), ("PortNames", C.POINTER(C.c_char_p)),
+                     ("PortRangeHints", C.c_void_p), ("ImplementationData", C.c_void_p),
+                     ("instantiate", C.CFUNCTYPE(HANDLE, C.POINTER(Desc), C.c_ulong)),
+                     ("connect_port", C.CFUNCTYPE(None, HANDLE, C.c_ulong, C.POINTER(C.c_float))),
+                     ("activate", C.c_void_p), ("run", C.CFUNCTYPE(None, HANDLE, C.c_ulong)), ("run_adding", C.c_void_p),
+                     ("set_run_adding_gain", C.c_void_p), ("deactivate", C.c_void_p), ("cleanup", C.CFUNCTYPE(None, HANDLE))]
+    L = C.CDLL(LADSPA)          # the constructor reads the config directory
+    L.ladspa_descriptor.restype = C.POINTER(Desc)
+    L.ladspa_descriptor.argtypes = [C.c_ulong]
+    d = L.ladspa_descriptor(0)
+    assert d and d.contents.PortCount == 4 and d.contents.Label == b"ladspa_dsp"
+    inst = d.contents.instantiate(d, 48000)
+    assert inst
+    n, nblk = 1000, 6
+    rng = np.random.default_rng(12)
+    x = (rng.standard_normal((n * nblk, 2)) * 0.2).astype(np.float32)
+    ports = [np.zeros(n, dtype=np.float32) for _ in range(4)]
+    for i, p in enumerate(ports):
+        d.contents.connect_port(inst, i, p.ctypes.data_as(C.POINTER(C.c_float)))
+    outs = []
+    for b in range(nblk):
+        ports[0][:] = x[b * n:(b + 1) * n, 0]
+        ports[1][:] = x[b * n:(b + 1) * n, 1]
+        d.contents.run(inst, n)
+        outs.append(np.stack([ports[2].copy(), ports[3].copy()], axis=1))
+    d.contents.cleanup(inst)
+    got = np.concatenate(outs).astype(np.float64)
+    if have_ref:
+        r = dropin.RefChain(chain, 48000, 2)
+        want = np.concatenate([r.run(x[b * n:(b + 1) * n].astype(np.float64)) for b in range(nblk)])
+        r.close()
+        assert got.shape == want.shape
+        assert rms(got - want.astype(np.float32).astype(np.float64)) <= 1e-7      # float32 ports
