@@ -675,6 +675,15 @@ int dspb200_chain_join(dspb200_chain *c, int shard, void *stream)
 	return 0;
 }
 
+int dspb200_debug_read(dspb200_chain *c, int shard, int op_index, long long *out, int max)
+{
+	if (!c || shard < 0 || shard >= (int) c->shards.size() || !out) return -1;
+	Shard *s = c->shards[shard].get();
+	if (op_index < 0 || op_index >= (int) s->ops.size()) return -1;
+	CUDA_TRY(cudaSetDevice(s->device), return -1);
+	return s->ops[op_index]->debug_read(out, max);
+}
+
 long dspb200_chain_drain_host(dspb200_chain *c, long frames, double *out)
 {
 	// the drain2 half of drain_effects_chain(), effects_chain.c:1199-1217

@@ -113,6 +113,12 @@ struct Op {
 		(void) st;
 		return 0;
 	}
+	// measurement hook (dspb200_debug_read): operator-specific counters, returns how many were written
+	virtual int debug_read(long long *out, int max)
+	{
+		(void) out; (void) max;
+		return 0;
+	}
 };
 
 // twiddle table exp(-2 pi i t / (2N)), t in [0, 2N), resident on the current device

@@ -590,13 +590,14 @@ struct MacBatchArgs {
 	int n_slots;
 	long h_ch_stride;
 	int pf;               // partitions 0..pf-1 are summed by the level's fused FFT kernel (1: upper levels, 2: level 0)
+	int s_first, s_step;  // channel of blockIdx.y: s_first + blockIdx.y * s_step (0, 1: all channels)
 };
 
 template <int T, bool SHARED_H>
 __global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_batch(MacBatchArgs a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	const int s = blockIdx.y;
+	const int s = a.s_first + blockIdx.y * a.s_step;
 	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
 	const bool dc = (k == 0);
@@ -1036,6 +1037,9 @@ struct FirOp : Op {
 	int pipe_pf = 0;
 	int pipe_evict_first = getenv("DSP_B200_FIR_PIPE_EVICT") ? atoi(getenv("DSP_B200_FIR_PIPE_EVICT")) : 1;
 	int pipe_fake_io = getenv("DSP_B200_FIR_PIPE_FAKEIO") ? atoi(getenv("DSP_B200_FIR_PIPE_FAKEIO")) : 0;   // measurement only
+	int pipe_no_items = getenv("DSP_B200_FIR_PIPE_NOITEMS") ? atoi(getenv("DSP_B200_FIR_PIPE_NOITEMS")) : 0;   // measurement only
+	long long *d_stats = nullptr;        // DSP_B200_FIR_PIPE_STATS: per-CTA cycle counters of the last pipeline launch
+	bool last_block_piped = false;
 	int batch_threads = getenv("DSP_B200_FIR_BATCH_THREADS") ? atoi(getenv("DSP_B200_FIR_BATCH_THREADS")) : 256;
 	cudaEvent_t ev_tail[2] = { nullptr, nullptr };
 	double *d_ring = nullptr, *d_ltmp = nullptr;
@@ -1098,6 +1102,7 @@ struct FirOp : Op {
 		dev_free(d_ch_map); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp);
 		dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi);
+		dev_free(d_stats);
 	}
 
 	int plan(long hint, cudaStream_t st)
@@ -1173,17 +1178,23 @@ struct FirOp : Op {
 				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
 				int tb = FIR_T_BATCH;
 				if (const char *e = getenv("DSP_B200_FIR_T")) tb = (atoi(e) == 8) ? 8 : (atoi(e) == 6) ? 6 : 4;
+				if (use_pipe) tb = PIPE_TB;   // the pipeline kernel's batch depth is compiled in (one channel residue per block)
 				if (L.P >= 2 * tb + pf + 1 && !(nb && nb[0] == '1')) {
 					t_batch = tb;
 					d_V = dev_alloc<double2>((size_t) 2 * t_batch * n_sel * L.B);
 					if (!d_V) return -1;
-					int lo = 0, hi = 0;
-					cudaDeviceGetStreamPriorityRange(&lo, &hi);
-					CUDA_TRY(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, lo), return -1);
-					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[0], cudaEventDisableTiming), return -1);
-					CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[1], cudaEventDisableTiming), return -1);
+					if (!use_pipe) {
+						int lo = 0, hi = 0;
+						cudaDeviceGetStreamPriorityRange(&lo, &hi);
+						CUDA_TRY(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, lo), return -1);
+						CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[0], cudaEventDisableTiming), return -1);
+						CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[1], cudaEventDisableTiming), return -1);
+					}
 				}
-				if (use_pipe) pipe_pf = (t_batch > 0) ? t_batch + 2 : L.P;
+				if (use_pipe) {
+					pipe_pf = (t_batch > 0) ? t_batch + 2 : L.P;
+					if (getenv("DSP_B200_FIR_PIPE_STATS")) d_stats = dev_alloc<long long>(8 * 1024);
+				}
 			}
 			if (L.B > Bmax) Bmax = L.B;
 		}
@@ -1231,6 +1242,15 @@ struct FirOp : Op {
 		h_taps.shrink_to_fit();
 		planned = true;
 		return 0;
+	}
+
+	int debug_read(long long *out, int max) override
+	{
+		if (!d_stats || max <= 0) return 0;
+		const int n = (max < 8 * 1024) ? max : 8 * 1024;
+		cudaDeviceSynchronize();
+		if (cudaMemcpy(out, d_stats, (size_t) n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+		return n;
 	}
 
 	int join(cudaStream_t st) override
@@ -1350,6 +1370,7 @@ struct FirOp : Op {
 				b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
 				b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 				b.pf = 1;
+				b.s_first = 0; b.s_step = 1;
 				const int threads = (L.B < 256) ? L.B : 256;
 				dim3 grid(L.B / threads, n_sel);
 				launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
@@ -1375,13 +1396,21 @@ struct FirOp : Op {
 		cudaStream_t ts = on_main ? st : side, bs = serial ? st : side2;
 		const long q = L.blk - 1, j = q + 2;
 		if (use_pipe) {
-			// the pipeline kernel sums partitions 0 .. pipe_pf-1 itself: only the batched V is produced ahead of time
-			if (t_batch > 0 && q % t_batch == 0) {
-				if (!serial) {
-					CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
-					CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
+			// The pipeline kernel of block q does block q's share of the batched tail itself (channels of residue
+			// q % 4: V_{q+2} .. V_{q+5} from the blocks up to q-1).  A block that took the general path gets the same
+			// share from the stand-alone batch kernel, here, on the caller's stream.
+			if (t_batch > 0 && !last_block_piped && q >= 1) {
+				const int g = (int) (q % t_batch);
+				if (n_sel > g) {
+					MacBatchArgs b = {};
+					b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q - 1; b.n_slots = 2 * t_batch;
+					b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+					b.pf = 2;
+					b.s_first = g; b.s_step = t_batch;
+					const int threads = (L.B < 256) ? L.B : 256;
+					dim3 grid(L.B / threads, (n_sel - g + t_batch - 1) / t_batch);
+					launch_mac_batch(t_batch, fc == 1, grid, threads, st, b);
 				}
-				if (launch_batch0(L, q, bs)) return -1;
 			}
 			return 0;
 		}
@@ -1414,6 +1443,7 @@ struct FirOp : Op {
 		b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
 		b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 		b.pf = 2;
+		b.s_first = 0; b.s_step = 1;
 		int threads = (batch_threads == 128 || batch_threads == 64) ? batch_threads : 256;
 		if (L.B < threads) threads = L.B;
 		dim3 grid(L.B / threads, n_sel);
@@ -1427,7 +1457,7 @@ struct FirOp : Op {
 	// (launched after block T*floor((blk-3)/T)) still reads until then.
 	int wait_batch_for(long blk, cudaStream_t st)
 	{
-		if (t_batch > 0 && tail_pf == 2 && blk >= 3 && !g_fir_serialize.load(std::memory_order_relaxed))
+		if (t_batch > 0 && tail_pf == 2 && !use_pipe && blk >= 3 && !g_fir_serialize.load(std::memory_order_relaxed))
 			CUDA_TRY(cudaStreamWaitEvent(st, ev_batch[((blk - 3) / t_batch) & 1], 0), return -1);
 		return 0;
 	}
@@ -1562,24 +1592,26 @@ struct FirOp : Op {
 			}
 			if (pos == 0 && seg == B0) {
 				// fast path: one whole aligned block
+				last_block_piped = false;
 				if (use_pipe && direct) {
-					if (wait_batch_for(L0.blk, st)) return -1;
 					PipeArgs f = {};
 					f.xin = src; f.xin_stride = C; f.xin_map = d_ch_map;
 					f.yout = d; f.yout_stride = dstride; f.yout_map = dmap;
 					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.R * B0; f.fdl_rows = L0.R; f.slot = (int) (L0.blk % L0.R);
 					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
-					f.pf = pipe_pf;
-					f.V = (t_batch > 0 && L0.blk >= 3) ? d_V + (size_t) (L0.blk % (2 * t_batch)) * n_sel * B0 : nullptr;
+					f.P = L0.P; f.pf = pipe_pf;
+					f.V = (t_batch > 0) ? d_V : nullptr; f.v_slots = 2 * t_batch; f.blk = L0.blk;
 					f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
 					f.evict_first = pipe_evict_first;
 					f.fake_io = (pipe_fake_io && C == n_sel && dstride == C) ? 1 : 0;
+					f.no_batch_items = pipe_no_items;
+					f.stats = d_stats;
 					if (launch_pipe(B0, f, st)) return -1;
 					++L0.blk;
+					last_block_piped = true;
 				}
 				else if (use_pipe) {
 					// a whole block that cannot use the direct form (never happens today: direct_io is a plan-time switch)
-					if (wait_batch_for(L0.blk, st)) return -1;
 					if (level_block(L0, d_ytmp, B0, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
 				}
 				else if (L0.P <= 2 || tail_pf == 2) {
@@ -1619,6 +1651,7 @@ struct FirOp : Op {
 				       d, dstride, dmap, B0, pos, seg);
 				if (pos + seg == B0) {
 					// block complete: X into the FDL, carry = IRFFT(S)[B:2B) (its first half has been emitted already)
+					last_block_piped = false;
 					if (wait_batch_for(L0.blk, st)) return -1;
 					if (level_block(L0, nullptr, 0, INV_UPDATE_CARRY, st)) return -1;
 					pre_valid = false;

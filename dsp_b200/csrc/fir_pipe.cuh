@@ -1,21 +1,29 @@
-// fir_pipe.cuh -- K2's block kernel as a persistent, warp-specialised pipeline (single-level plans).
+// fir_pipe.cuh -- K2's block kernel as ONE persistent, warp-specialised pipeline per block (single-level plans).
 //
-// One CTA per SM walks the channels s = blockIdx.x, blockIdx.x + gridDim.x, ...; for the block j of channel s
-//     S = X_j H_0 + sum_{1 <= p < pf} X_{j-p} H_p + V_j        (reference: fft_part_group_compute, fir_p.c:64-103)
-//     y = IRFFT(S)[0:B) + carry,  carry' = IRFFT(S)[B:2B)
-// with three kinds of warps that only meet at mbarriers:
-//   producer (1 warp, one lane)  streams the FDL rows X_{j-p}, the filter rows H_p and V_j of the CTA's channels
-//                                from HBM into a ring of shared-memory stages with cp.async.bulk (TMA bulk copies,
-//                                completion counted in bytes on the stage's "full" mbarrier) -- it runs ahead of
-//                                everybody else, across channel boundaries, limited only by the ring
-//   MAC warps (4)                multiply-accumulate the stages into registers (512 bins per stage, 4 per lane) and
-//                                drop the finished sums into the spectrum buffer `sbuf`
-//   transform team (N/16 threads) reads the caller's interleaved block, forward FFT in shared memory, spectrum to
-//                                the FDL, S = sbuf + X_j H_0 for the bin pairs it owns, inverse FFT in place,
-//                                overlap-add, writes the caller's interleaved result
-// The HBM stream (everything but 8 + 16 + 24 of the bytes per sample) therefore never waits for a transform and
-// the transforms never wait for a load they did not issue a whole phase earlier.  sbuf is handed back and forth
-// by two mbarriers (s_full: MAC -> team, s_empty: team -> MAC); the team synchronises itself with a named barrier.
+// One CTA per SM.  For block j the launch does ALL the device work of the block:
+//   (a) per channel s (s = blockIdx.x, blockIdx.x + gridDim.x, ...):
+//         S = X_j H_0 + sum_{1 <= p < pf} X_{j-p} H_p + V_j        (reference: fft_part_group_compute, fir_p.c:64-103)
+//         y = IRFFT(S)[0:B) + carry,  carry' = IRFFT(S)[B:2B)
+//   (b) the time-batched tail for a QUARTER of the channels (those with s % 4 == j % 4):
+//         V_{j+2+t} = sum_{p >= pf} X_{j+2+t-p} H_p,  t = 0..3      -- only blocks <= j-1 are involved, so nothing in
+//       this launch depends on anything else in it; every FDL and filter row is streamed once for four outputs (the
+//       filter rows slide through a register window).  Spreading the batch over the channels' residues makes every
+//       launch the same work: no side streams, no events, one kernel per block.
+// Three kinds of warps that only meet at mbarriers:
+//   producer (1 warp, one lane)   the scheduler: streams row chunks from HBM into a ring of shared-memory stages with
+//                                 cp.async.bulk (TMA bulk copies, completion counted in bytes on the stage's "full"
+//                                 mbarrier) and tags every stage with a command word.  It issues the stages of (a) as
+//                                 soon as the spectrum buffer `sbuf` is free for the channel and fills all other time
+//                                 with its share of the work items of (b) -- the HBM stream never waits for a transform.
+//   MAC warps (8)                 execute the command of each stage: complex multiply-accumulate of 512 bins (2 per
+//                                 lane) into registers, sums of (a) dropped into `sbuf`, sums of (b) stored to V
+//   transform team (N/16 threads) reads the caller's interleaved block, forward FFT in shared memory, spectrum to the
+//                                 FDL, S = sbuf + X_j H_0 for the bin pairs it owns, inverse FFT in place,
+//                                 overlap-add, writes the caller's interleaved result.  It is latency-bound (two
+//                                 warps per scheduler) -- and that no longer matters: the kernel's duration is set by
+//                                 the byte stream, which runs beside it at the speed of the HBM.
+// sbuf is handed back and forth by two mbarriers (s_full: MAC -> team, s_empty: team -> producer); the team synchronises
+// itself with a named barrier.
 #pragma once
 #include "common.cuh"
 #include "fft.cuh"
@@ -23,10 +31,12 @@
 
 namespace dspb200 {
 
+constexpr int PIPE_TB = 4;   // batch depth of (b): outputs per pass, = number of channel residues
+
 template <int N>
 struct PipeCfg {
 	static constexpr int TF = N / 16;                 // transform team (one FFT)
-	static constexpr int MAC_WARPS = 4;
+	static constexpr int MAC_WARPS = 8;
 	static constexpr int TM = MAC_WARPS * 32;
 	static constexpr int THREADS = TF + TM + 32;      // + producer warp
 	static constexpr int CHUNK = 512;                 // bins per stage
@@ -36,7 +46,8 @@ struct PipeCfg {
 	static constexpr size_t STAGE_BYTES = 2 * (size_t) CHUNK * sizeof(double2);   // X chunk | H chunk
 	static constexpr size_t FBUF = (size_t) FftCfg<N>::STRIDE * sizeof(double2);
 	static constexpr size_t SBUF = (size_t) N * sizeof(double2);
-	static constexpr size_t SMEM = FBUF + SBUF + NS * STAGE_BYTES + (2 * NS + 2) * sizeof(uint64_t);
+	static constexpr size_t CMDS = (size_t) NS * sizeof(int4);
+	static constexpr size_t SMEM = FBUF + SBUF + NS * STAGE_BYTES + CMDS + (2 * NS + 2) * sizeof(uint64_t);
 	static_assert(TF % 32 == 0 && N % CHUNK == 0 && CHUNK % TM == 0, "shape");
 };
 
@@ -52,13 +63,32 @@ struct PipeArgs {
 	int fdl_rows, slot;      // slot = row of block j
 	const double2 *H;        // [s or 0][P][N]
 	long h_ch_stride;        // 0: shared filter
-	int pf;                  // partitions summed here: 0 .. pf-1
-	const double2 *V;        // [s][N] spectrum of the older partitions for block j (NULL: none)
+	int P;                   // partitions of the filter
+	int pf;                  // partitions summed in (a): 0 .. pf-1
+	double2 *V;              // [v_slots][n_ch][N]: batched spectra, slot = block index % v_slots (NULL: no batching, pf == P)
+	int v_slots;
+	long blk;                // j
 	double *carry;           // [s][N]
 	const double2 *tw, *ptw;
 	int n_ch;
 	int evict_first;         // streaming operands are read once per block: keep them from displacing the rest of L2
 	int fake_io;             // MEASUREMENT ONLY (DSP_B200_FIR_PIPE_FAKEIO): contiguous block I/O (wrong results) to time the kernel without the strided accesses
+	int no_batch_items;      // MEASUREMENT ONLY: skip (b)
+	long long *stats;        // MEASUREMENT ONLY: [gridDim.x][8] cycle counters (NULL: off)
+};
+
+// stage commands (producer -> MAC warps)
+enum {
+	PC_SZERO = 1,      // (a): clear the sum
+	PC_SMAC = 2,       //      sum += X . H
+	PC_SADDV = 4,      //      sum += the chunk in the X slot (V_j)
+	PC_SSTORE = 8,     //      sum -> sbuf[chunk]
+	PC_SFULL = 16,     //      last chunk of the channel: sbuf is complete
+	PC_BINIT = 32,     // (b): clear the four sums and the window; window[3] = chunk in the H slot (PC_BHASH)
+	PC_BSTEP = 64,     //      sums[t] += X . window[t]; window slides; window[3] = chunk in the H slot (PC_BHASH) or 0
+	PC_BHASH = 128,
+	PC_BSTORE = 256,   //      sums -> V[(j + 2 + t) % v_slots][s][chunk]
+	PC_EXIT = 512
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) -------------------------------------------
@@ -129,22 +159,23 @@ __device__ __forceinline__ void pipe_prefetch_rows(const void *p, long bytes, in
 	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
-// Register cap: 416 threads x 104 registers leave room for one 256-thread CTA of the batched MAC kernel on the same
-// SM, so that the HBM stream of the look-ahead MAC fills the time this kernel's transform team spends on latency.
+// Register cap: 544 threads x 120 registers = the register file of an SM (one CTA per SM).
 #ifndef FIR_PIPE_MAXNREG
-#define FIR_PIPE_MAXNREG 104
+#define FIR_PIPE_MAXNREG 120
 #endif
+
 template <int N>
 __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 {
 	using Cfg = PipeCfg<N>;
-	constexpr int T = Cfg::TF, CHUNK = Cfg::CHUNK, NS = Cfg::NS, PER = Cfg::PER, TM = Cfg::TM;
+	constexpr int T = Cfg::TF, CHUNK = Cfg::CHUNK, NS = Cfg::NS, PER = Cfg::PER, TM = Cfg::TM, TB = PIPE_TB;
 	using TeamSync = NamedSync<1, T>;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double2 *fbuf = reinterpret_cast<double2 *>(smem_raw);
 	double2 *sbuf = reinterpret_cast<double2 *>(smem_raw + Cfg::FBUF);
 	double2 *ring = reinterpret_cast<double2 *>(smem_raw + Cfg::FBUF + Cfg::SBUF);
-	uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Cfg::FBUF + Cfg::SBUF + NS * Cfg::STAGE_BYTES);
+	int4 *cmds = reinterpret_cast<int4 *>(smem_raw + Cfg::FBUF + Cfg::SBUF + NS * Cfg::STAGE_BYTES);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Cfg::FBUF + Cfg::SBUF + NS * Cfg::STAGE_BYTES + Cfg::CMDS);
 	uint64_t *full = bars, *empty = bars + NS, *s_full = bars + 2 * NS, *s_empty = bars + 2 * NS + 1;
 
 	if (threadIdx.x == 0) {
@@ -159,6 +190,8 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 	__syncthreads();   // the only CTA-wide barrier: from here on the roles meet at mbarriers
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const bool stats_on = a.stats != nullptr;
+	long long t_begin = stats_on ? clock64() : 0, t_wait = 0;
 
 	if (warp < T / 32) {
 		// ------------------------------------------------------------------------------------------
@@ -218,7 +251,11 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 				}
 			}
 			// (2) S = X_j H_0 + (what the MAC warps summed for this channel), inverse merge into shared memory
-			mbar_wait(s_full, (unsigned) (it & 1));
+			{
+				const long long t0 = stats_on ? clock64() : 0;
+				mbar_wait(s_full, (unsigned) (it & 1));
+				if (stats_on) t_wait += clock64() - t0;
+			}
 #pragma unroll
 			for (int i = 0; i < 8; ++i) {
 				const int k = t + i * T;
@@ -265,89 +302,232 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			// entry n and n + N/2 of buf are only touched by this thread between the last pass and the next
 			// channel's first barrier: no barrier needed here
 		}
+		if (stats_on && threadIdx.x == 0) {
+			a.stats[blockIdx.x * 8 + 0] = t_wait;
+			a.stats[blockIdx.x * 8 + 3] = clock64() - t_begin;
+		}
 	}
 	else if (warp < T / 32 + Cfg::MAC_WARPS) {
 		// ------------------------------------------------------------------------------------------
-		// MAC warps
+		// MAC warps: execute the stages' commands
 		// ------------------------------------------------------------------------------------------
 		const int tm = threadIdx.x - T;
 		int stage = 0;
 		unsigned phase = 0;
-		int it = 0;
-		for (int s = blockIdx.x; s < a.n_ch; s += gridDim.x, ++it) {
-			mbar_wait(s_empty, (unsigned) ((it & 1) ^ 1));   // the team has taken the previous channel's sums
-			for (int c = 0; c < Cfg::NCHUNK; ++c) {
-				double2 acc[PER];
+		const double2 zero = make_double2(0.0, 0.0);
+		double2 accS[PER], accB[TB][PER], hw[TB][PER];
 #pragma unroll
-				for (int i = 0; i < PER; ++i) acc[i] = make_double2(0.0, 0.0);
-				const bool dc = (c == 0 && tm == 0);
-				for (int p = 1; p < a.pf; ++p) {
-					mbar_wait(&full[stage], phase);
-					const double2 *Xs = ring + (size_t) stage * 2 * CHUNK, *Hs = Xs + CHUNK;
+		for (int i = 0; i < PER; ++i) {
+			accS[i] = zero;
+#pragma unroll
+			for (int u = 0; u < TB; ++u) { accB[u][i] = zero; hw[u][i] = zero; }
+		}
+		for (;;) {
+			{
+				const long long t0 = stats_on ? clock64() : 0;
+				mbar_wait(&full[stage], phase);
+				if (stats_on) t_wait += clock64() - t0;
+			}
+			const int4 cmd = cmds[stage];
+			const int fl = cmd.x, chunk = cmd.y, s = cmd.z;
+			if (fl & PC_EXIT) break;
+			const double2 *Xs = ring + (size_t) stage * 2 * CHUNK, *Hs = Xs + CHUNK;
+			const bool dc = (chunk == 0 && tm == 0);   // bin 0 packs (DC, Nyquist): two real products
+			if (fl & (PC_SZERO | PC_SMAC | PC_SADDV | PC_SSTORE)) {
+				if (fl & PC_SZERO) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) accS[i] = zero;
+				}
+				if (fl & PC_SMAC) {
 					double2 x[PER], h[PER];
 #pragma unroll
 					for (int i = 0; i < PER; ++i) { x[i] = Xs[tm + i * TM]; h[i] = Hs[tm + i * TM]; }
 					if (dc) {
-						acc[0].x = fma(x[0].x, h[0].x, acc[0].x);
-						acc[0].y = fma(x[0].y, h[0].y, acc[0].y);
+						accS[0].x = fma(x[0].x, h[0].x, accS[0].x);
+						accS[0].y = fma(x[0].y, h[0].y, accS[0].y);
 					}
-					else acc[0] = pipe_cmac(acc[0], x[0], h[0]);
+					else accS[0] = pipe_cmac(accS[0], x[0], h[0]);
 #pragma unroll
-					for (int i = 1; i < PER; ++i) acc[i] = pipe_cmac(acc[i], x[i], h[i]);
-					__syncwarp();
-					if (lane == 0) mbar_arrive(&empty[stage]);
-					if (++stage == NS) { stage = 0; phase ^= 1; }
+					for (int i = 1; i < PER; ++i) accS[i] = pipe_cmac(accS[i], x[i], h[i]);
 				}
-				if (a.V) {
-					mbar_wait(&full[stage], phase);
-					const double2 *Vs = ring + (size_t) stage * 2 * CHUNK;
+				if (fl & PC_SADDV) {
 #pragma unroll
 					for (int i = 0; i < PER; ++i) {
-						const double2 v = Vs[tm + i * TM];
-						acc[i].x += v.x; acc[i].y += v.y;
+						const double2 v = Xs[tm + i * TM];
+						accS[i].x += v.x; accS[i].y += v.y;
 					}
-					__syncwarp();
-					if (lane == 0) mbar_arrive(&empty[stage]);
-					if (++stage == NS) { stage = 0; phase ^= 1; }
 				}
+				if (fl & PC_SSTORE) {
 #pragma unroll
-				for (int i = 0; i < PER; ++i) sbuf[c * CHUNK + tm + i * TM] = acc[i];
+					for (int i = 0; i < PER; ++i) sbuf[chunk * CHUNK + tm + i * TM] = accS[i];
+				}
+			}
+			else {
+				if (fl & PC_BINIT) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) {
+#pragma unroll
+						for (int u = 0; u < TB; ++u) { accB[u][i] = zero; hw[u][i] = zero; }
+						if (fl & PC_BHASH) hw[TB - 1][i] = Hs[tm + i * TM];
+					}
+				}
+				if (fl & PC_BSTEP) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) {
+						const double2 x = Xs[tm + i * TM];
+						const double2 hn = (fl & PC_BHASH) ? Hs[tm + i * TM] : zero;
+						if (dc && i == 0) {
+#pragma unroll
+							for (int u = 0; u < TB; ++u) {
+								accB[u][i].x = fma(x.x, hw[u][i].x, accB[u][i].x);
+								accB[u][i].y = fma(x.y, hw[u][i].y, accB[u][i].y);
+							}
+						}
+						else {
+#pragma unroll
+							for (int u = 0; u < TB; ++u) accB[u][i] = pipe_cmac(accB[u][i], x, hw[u][i]);
+						}
+#pragma unroll
+						for (int u = 0; u + 1 < TB; ++u) hw[u][i] = hw[u + 1][i];
+						hw[TB - 1][i] = hn;
+					}
+				}
+				if (fl & PC_BSTORE) {
+#pragma unroll
+					for (int u = 0; u < TB; ++u) {
+						const long slot = (a.blk + 2 + u) % a.v_slots;
+						double2 *Vd = a.V + (slot * a.n_ch + s) * (long) N + chunk * CHUNK;
+#pragma unroll
+						for (int i = 0; i < PER; ++i) Vd[tm + i * TM] = accB[u][i];
+					}
+				}
 			}
 			__syncwarp();
-			if (lane == 0) mbar_arrive(s_full);
+			if (lane == 0) {
+				if (fl & PC_SFULL) mbar_arrive(s_full);   // after this warp's part of the last chunk is in sbuf
+				mbar_arrive(&empty[stage]);
+			}
+			if (++stage == NS) { stage = 0; phase ^= 1; }
+		}
+		if (stats_on && tm == 0) {
+			a.stats[blockIdx.x * 8 + 1] = t_wait;
+			a.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
 		}
 	}
 	else if (lane == 0) {
 		// ------------------------------------------------------------------------------------------
-		// producer
+		// producer / scheduler
 		// ------------------------------------------------------------------------------------------
 		const uint64_t pol = l2_policy_evict_first();
 		const bool hint_x = a.evict_first != 0, hint_h = a.evict_first != 0 && a.h_ch_stride != 0;
+		constexpr unsigned ROW_BYTES = CHUNK * sizeof(double2);
+		constexpr int NCHUNK = Cfg::NCHUNK;
+		const int G = (int) gridDim.x, b = (int) blockIdx.x;
+		const int n_my = (b < a.n_ch) ? (a.n_ch - b + G - 1) / G : 0;   // channels of this CTA
+		const bool has_v = a.V != nullptr && a.blk >= 3;                 // V_j exists (zero before block 3: not read)
 		int stage = 0;
 		unsigned phase = 0;
-		constexpr unsigned ROW_BYTES = CHUNK * sizeof(double2);
-		for (int s = blockIdx.x; s < a.n_ch; s += gridDim.x) {
+		long n_stages = 0;
+
+		// one stage: wait for the slot, tag it, start the copies
+		auto emit = [&](int flags, int chunk, int s, const double2 *xsrc, const double2 *hsrc, bool hx, bool hh) {
+			{
+				const long long t0 = stats_on ? clock64() : 0;
+				mbar_wait(&empty[stage], phase ^ 1);
+				if (stats_on) t_wait += clock64() - t0;
+			}
+			cmds[stage] = make_int4(flags, chunk, s, 0);
+			double2 *dst = ring + (size_t) stage * 2 * CHUNK;
+			const unsigned bytes = (xsrc ? ROW_BYTES : 0) + (hsrc ? ROW_BYTES : 0);
+			if (bytes) mbar_arrive_expect_tx(&full[stage], bytes);
+			else mbar_arrive(&full[stage]);   // nothing to copy (exit, or a row that does not exist)
+			if (xsrc) bulk_g2s(dst, xsrc, ROW_BYTES, &full[stage], hx, pol);
+			if (hsrc) bulk_g2s(dst + CHUNK, hsrc, ROW_BYTES, &full[stage], hh, pol);
+			if (++stage == NS) { stage = 0; phase ^= 1; }
+			++n_stages;
+		};
+
+		// (b): the channels s = g + TB k of this block's residue g, cut into NCHUNK items each; this CTA's share
+		// is weighted by what (a) leaves it (CTAs that walk fewer channels take more items)
+		long item = 0, item_end = 0, item0 = 0;
+		const int g = (int) (a.blk % TB);
+		const int n_g = (a.V && a.blk >= 1 && a.n_ch > g && !a.no_batch_items) ? (a.n_ch - g + TB - 1) / TB : 0;
+		if (n_g > 0) {
+			const long n_items = (long) n_g * NCHUNK;
+			const long Ss = (long) NCHUNK * (a.pf - 1 + (has_v ? 1 : 0)), Sb = a.P - 2;
+			const long total = (long) a.n_ch * Ss + n_items * Sb;
+			const long target = (total + G - 1) / G;
+			long W = 0, Wb = 0, wb = 0;
+			for (int c = 0; c < G; ++c) {
+				const int nc = (c < a.n_ch) ? (a.n_ch - c + G - 1) / G : 0;
+				long wgt = target - nc * Ss;
+				if (wgt < 1) wgt = 1;
+				if (c < b) Wb += wgt;
+				if (c == b) wb = wgt;
+				W += wgt;
+			}
+			item0 = item = n_items * Wb / W;
+			item_end = n_items * (Wb + wb) / W;
+		}
+
+		auto emit_item = [&](long it_) {
+			const int k = (int) (it_ / NCHUNK), c = (int) (it_ % NCHUNK);
+			const int s = g + TB * k;
+			const double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride + c * CHUNK;
+			const double2 *Hc = a.H + (long) s * a.h_ch_stride + c * CHUNK;
+			// window[t] = H_{3+t} where it belongs to the batch (p >= pf): with pf = TB + 2 only t = TB-1 does
+			const int p0 = a.pf;
+			emit(PC_BINIT | ((p0 < a.P) ? PC_BHASH : 0), c, s, nullptr, (p0 < a.P) ? Hc + (long) p0 * N : nullptr, false, hint_h);
+			// step m: X_{j+2-m} (row slot-1-(m-3)... relative to this block's row) meets window; next window row H_{m+TB}
+			for (int m = 3; m < a.P; ++m) {
+				int sl = a.slot - (m - 2);              // row of block j - (m - 2) = (j - 1) + 3 - m
+				sl %= a.fdl_rows;
+				if (sl < 0) sl += a.fdl_rows;
+				const int hn = m + TB;
+				const bool hh = hn < a.P;
+				emit(PC_BSTEP | (hh ? PC_BHASH : 0) | ((m == a.P - 1) ? PC_BSTORE : 0), c, s, fdl + (long) sl * N,
+				     hh ? Hc + (long) hn * N : nullptr, hint_x, hint_h);
+			}
+		};
+
+		auto emit_channel = [&](int s) {
 			const double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride;
 			const double2 *Hc = a.H + (long) s * a.h_ch_stride;
-			const double2 *Vc = a.V ? a.V + (long) s * N : nullptr;
-			for (int c = 0; c < Cfg::NCHUNK; ++c) {
+			const double2 *Vc = has_v ? a.V + ((a.blk % a.v_slots) * a.n_ch + s) * (long) N : nullptr;
+			for (int c = 0; c < NCHUNK; ++c) {
+				const int last = (c == NCHUNK - 1) ? PC_SFULL : 0;
+				if (a.pf <= 1 && !Vc) { emit(PC_SZERO | PC_SSTORE | last, c, s, nullptr, nullptr, false, false); continue; }
 				for (int p = 1; p < a.pf; ++p) {
 					int sl = a.slot - p;
 					if (sl < 0) sl += a.fdl_rows;
-					mbar_wait(&empty[stage], phase ^ 1);
-					mbar_arrive_expect_tx(&full[stage], 2 * ROW_BYTES);
-					double2 *dst = ring + (size_t) stage * 2 * CHUNK;
-					bulk_g2s(dst, fdl + (long) sl * N + c * CHUNK, ROW_BYTES, &full[stage], hint_x, pol);
-					bulk_g2s(dst + CHUNK, Hc + (long) p * N + c * CHUNK, ROW_BYTES, &full[stage], hint_h, pol);
-					if (++stage == NS) { stage = 0; phase ^= 1; }
+					int fl = PC_SMAC | (p == 1 ? PC_SZERO : 0);
+					if (p == a.pf - 1 && !Vc) fl |= PC_SSTORE | last;
+					emit(fl, c, s, fdl + (long) sl * N + c * CHUNK, Hc + (long) p * N + c * CHUNK, hint_x, hint_h);
 				}
-				if (Vc) {
-					mbar_wait(&empty[stage], phase ^ 1);
-					mbar_arrive_expect_tx(&full[stage], ROW_BYTES);
-					bulk_g2s(ring + (size_t) stage * 2 * CHUNK, Vc + c * CHUNK, ROW_BYTES, &full[stage], hint_x, pol);
-					if (++stage == NS) { stage = 0; phase ^= 1; }
-				}
+				if (Vc) emit(PC_SADDV | PC_SSTORE | last | (a.pf <= 1 ? PC_SZERO : 0), c, s, Vc + c * CHUNK, nullptr, hint_x, false);
 			}
+		};
+
+		int ci = 0;   // next channel of (a) to issue
+		for (;;) {
+			if (ci < n_my && (ci == 0 || mbar_try_wait(s_empty, (unsigned) ((ci & 1) ^ 1)))) {
+				emit_channel(b + ci * G);
+				++ci;
+			}
+			else if (item < item_end) emit_item(item++);
+			else if (ci < n_my) {
+				const long long t0 = stats_on ? clock64() : 0;
+				mbar_wait(s_empty, (unsigned) ((ci & 1) ^ 1));   // nothing else to do: wait for the team
+				if (stats_on) t_wait += clock64() - t0;
+			}
+			else break;
+		}
+		emit(PC_EXIT, 0, 0, nullptr, nullptr, false, false);
+		if (stats_on) {
+			a.stats[blockIdx.x * 8 + 2] = t_wait;
+			a.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;
+			a.stats[blockIdx.x * 8 + 6] = n_stages;
+			a.stats[blockIdx.x * 8 + 7] = item_end - item0;
 		}
 	}
 }

@@ -46,6 +46,7 @@ SIGNATURES = {
     "dspb200_chain_run_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]),
     "dspb200_chain_run_device": (C.c_long, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dspb200_chain_join": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dspb200_debug_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int]),
     "dspb200_chain_drain_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p]),
     "dspb200_chain_reset": (None, [C.c_void_p]),
     "dspb200_chain_sync": (C.c_int, [C.c_void_p]),
@@ -246,6 +247,12 @@ class Chain:
     def join(self, shard, stream=None):
         """Make `stream` wait for everything the shard's operators have enqueued on streams of their own."""
         _check(lib().dspb200_chain_join(self.h, int(shard), stream), "join")
+
+    def debug_read(self, shard=0, op_index=0, max_values=8 * 1024):
+        """Operator-specific device counters (measurement hook); numpy int64 array."""
+        buf = (C.c_longlong * max_values)()
+        n = lib().dspb200_debug_read(self.h, int(shard), int(op_index), buf, max_values)
+        return np.array(buf[:max(n, 0)], dtype=np.int64)
 
     def drain(self, frames):
         """One drain2 poll (resample.c:163-188); None when dry."""

@@ -127,6 +127,11 @@ long dspb200_chain_run_device(dspb200_chain *c, int shard, long frames, const do
  * calls made until now.  Not needed for correctness of later calls. */
 int  dspb200_chain_join(dspb200_chain *c, int shard, void *stream);
 
+/* Measurement hook: operator-specific device counters of operator `op_index` of shard `shard` (K2 with
+ * DSP_B200_FIR_PIPE_STATS=1: per-CTA cycle counters of the last pipeline launch, 8 per CTA: team wait, MAC wait,
+ * producer wait, team total, MAC total, producer total, stages, batch items).  Returns the count written. */
+int  dspb200_debug_read(dspb200_chain *c, int shard, int op_index, long long *out, int max);
+
 /* resample_effect_drain2() semantics (resample.c:163-188) for the whole chain: push zeros
  * until every rate-changing operator is dry.  Returns frames written (0..max_frames*ratio),
  * or -1 when nothing is left. */
