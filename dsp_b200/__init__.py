@@ -5,4 +5,4 @@ C shim under shim/ that exposes it through the reference's own `struct effect` s
 Python package is the thin binding used by tests and bench.py; it has no CPU path.
 """
 from .lib import (Chain, DspB200Error, debug_serialize, PinnedArray, biquad_design, device_count, hilbert_taps,  # noqa: F401
-                  kernel_launches, last_error, lib, profile_enable, profile_read, resample_params)
+                  kernel_launches, last_error, lib, profile_enable, profile_read, resample_params, copy_counts)

@@ -21,6 +21,7 @@ namespace dspb200 {
 // ------------------------------------------------------------------------------------------
 static thread_local char tls_error[512] = "";
 std::atomic<long long> g_kernel_launches{0};
+std::atomic<long long> g_h2d_copies{0}, g_d2h_copies{0};   // host<->device block copies issued (dspb200_copy_counts)
 
 void set_error(const char *fmt, ...)
 {
@@ -529,6 +530,33 @@ int dspb200_chain_add_fir(dspb200_chain *c, const char *selector, const double *
 	return 0;
 }
 
+int dspb200_chain_add_align(dspb200_chain *c, const long *delay, long discard_frames)
+{
+	if (!c || !delay || discard_frames < 0) { set_error("align: bad arguments"); return -1; }
+	FOR_EACH_SHARD(c, s) {
+		CUDA_TRY(cudaSetDevice(s->device), return -1);
+		Op *op = make_align_op(s->ch_count, c->out_fs, delay + s->ch_begin, discard_frames);
+		if (!op) return -1;
+		s->ops.emplace_back(op);
+	}
+	++c->n_ops;
+	return 0;
+}
+
+int dspb200_chain_inplace_ok(const dspb200_chain *c)
+{
+	if (!c || c->shards.empty()) return 1;
+	for (const auto &op : c->shards[0]->ops)
+		if (!op->inplace_ok) return 0;
+	return 1;
+}
+
+void dspb200_copy_counts(long long *h2d, long long *d2h)
+{
+	if (h2d) *h2d = g_h2d_copies.load();
+	if (d2h) *d2h = g_d2h_copies.load();
+}
+
 int dspb200_chain_add_resample(dspb200_chain *c, int out_fs, double bandwidth)
 {
 	if (!c) return -1;
@@ -577,6 +605,7 @@ static int copy_slab(const Shard &s, int C, long frames, double *dev, const doub
 {
 	const size_t w = (size_t) s.ch_count * sizeof(double), hp = (size_t) C * sizeof(double);
 	if (frames <= 0) return 0;
+	(host_in ? g_h2d_copies : g_d2h_copies).fetch_add(1, std::memory_order_relaxed);
 	if (host_in) {
 		if (s.ch_count == C) CUDA_TRY(cudaMemcpyAsync(dev, host_in, w * frames, cudaMemcpyHostToDevice, s.stream), return -1);
 		else CUDA_TRY(cudaMemcpy2DAsync(dev, w, host_in + s.ch_begin, hp, w, frames, cudaMemcpyHostToDevice, s.stream), return -1);

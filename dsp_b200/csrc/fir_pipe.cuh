@@ -159,9 +159,9 @@ __device__ __forceinline__ void pipe_prefetch_rows(const void *p, long bytes, in
 	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
-// Register cap: 544 threads x 120 registers = the register file of an SM (one CTA per SM).
+// Register cap: 17 warps x 32 x 112 registers = 60928 of the 65536 (registers are allocated per warp in units of 512: 120 would not fit).
 #ifndef FIR_PIPE_MAXNREG
-#define FIR_PIPE_MAXNREG 120
+#define FIR_PIPE_MAXNREG 112
 #endif
 
 template <int N>

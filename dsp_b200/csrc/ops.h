@@ -14,6 +14,8 @@ Op *fuse_biquad_ops(Op *a, Op *b);
 // k-th selected channel of this slab (ignored when filter_channels == 1)
 Op *make_fir_op(int slab_channels, int fs, const char *slab_selector, const double *taps, int filter_channels,
                 long filter_frames, const int *taps_cols, long latency, long block_hint, cudaStream_t st);
+// align.c:35-64 / delay.c:47-63: per-channel whole-sample delays (+ frames dropped at the head of the stream)
+Op *make_align_op(int slab_channels, int fs, const long *delay, long discard_frames);
 // resample.c
 Op *make_resample_op(int slab_channels, int fs_in, int fs_out, double bandwidth, cudaStream_t st);
 

@@ -41,6 +41,9 @@ SIGNATURES = {
     "dspb200_chain_add_gain": (C.c_int, [C.c_void_p, _dp, _dp]),
     "dspb200_chain_add_biquad": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "dspb200_chain_add_fir": (C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_int, C.c_long, C.c_long, C.c_long]),
+    "dspb200_chain_add_align": (C.c_int, [C.c_void_p, _lp, C.c_long]),
+    "dspb200_chain_inplace_ok": (C.c_int, [C.c_void_p]),
+    "dspb200_copy_counts": (None, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "dspb200_chain_add_resample": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "dspb200_chain_max_out_frames": (C.c_long, [C.c_void_p, C.c_long]),
     "dspb200_chain_run_host": (C.c_long, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]),
@@ -182,6 +185,12 @@ class Chain:
         _check(lib().dspb200_chain_add_fir(self.h, sel, _as_dp(taps), taps.shape[1], taps.shape[0], int(latency), int(block_hint)), "add_fir")
         return self
 
+    def add_align(self, delay, discard_frames=0):
+        """delay: per-channel whole-frame delays (align.c / delay.c); discard_frames dropped at the head of the stream."""
+        d = (C.c_long * self.channels)(*[int(v) for v in np.broadcast_to(np.asarray(delay), (self.channels,))])
+        _check(lib().dspb200_chain_add_align(self.h, d, int(discard_frames)), "add_align")
+        return self
+
     def add_resample(self, out_fs, bandwidth=0.0):
         _check(lib().dspb200_chain_add_resample(self.h, int(out_fs), float(bandwidth)), "add_resample")
         return self
@@ -305,6 +314,13 @@ class Chain:
             self.close()
         except Exception:
             pass
+
+
+def copy_counts():
+    """(host->device, device->host) block copies issued so far by this process."""
+    a, b = C.c_longlong(), C.c_longlong()
+    lib().dspb200_copy_counts(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def biquad_design(type_, fs, arg0, arg1=0.0, arg2=0.0, arg3=0.0, width_type=1):

@@ -98,6 +98,16 @@ int dspb200_chain_add_fir(dspb200_chain *c, const char *selector, const double *
  * (0 = default 0.939).  Emits exactly the frames resample_effect_run() would per call. */
 int dspb200_chain_add_resample(dspb200_chain *c, int out_fs, double bandwidth);
 
+/* align.c:35-64 / delay.c:47-63 -- channel k delayed by delay[k] >= 0 whole frames (0: untouched); the first
+ * discard_frames frames of the stream are dropped (align.c:53-62, CLI build): such a call returns fewer frames. */
+int dspb200_chain_add_align(dspb200_chain *c, const long *delay, long discard_frames);
+
+/* 1 when every operator may run in place (dspb200_chain_run_host with in == out keeps the frame count). */
+int dspb200_chain_inplace_ok(const dspb200_chain *c);
+
+/* How many host->device / device->host block copies (one per shard and call) the library has issued so far. */
+void dspb200_copy_counts(long long *h2d, long long *d2h);
+
 /* ---- running --------------------------------------------------------------------------- */
 /* Upper bound of output frames for `in_frames` input frames (effects_chain.c:993-1020). */
 long dspb200_chain_max_out_frames(const dspb200_chain *c, long in_frames);

@@ -17,6 +17,8 @@
 #include "util.h"
 #include "gpu_effect.h"
 
+struct effect * gpu_riir_effect_new(const struct effect_info *, const struct stream_info *, const char *, const struct biquad_state *, double);
+
 void biquad_reset(struct biquad_state *state)
 {
 	state->m0 = state->m1 = 0.0;
@@ -195,7 +197,7 @@ struct effect * biquad_effect_init(const struct effect_info *ei, const struct st
 	}
 
 	if (reverse)
-		return reverse_iir_effect_init_from_biquad(ei, istream, channel_selector, &b, thresh);
+		return gpu_riir_effect_new(ei, istream, channel_selector, &b, thresh);   /* shim/riir.c: the reference's design, the device's convolution */
 
 	const int C = istream->channels;
 	dspb200_chain *chain = gpu_chain_new(ei->name, istream);

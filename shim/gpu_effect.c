@@ -65,21 +65,73 @@ void gpu_part_free(struct gpu_part *p)
 	}
 }
 
-static sample_t * gpu_effect_run(struct effect *e, ssize_t *frames, sample_t *ibuf, sample_t *obuf)
+/* ---- device hand-off between neighbouring GPU effects --------------------------------------------------- */
+static void (*gpu_kinds[8])(struct effect *);
+static int n_gpu_kinds;
+
+void gpu_register_effect_kind(void (*destroy)(struct effect *))
+{
+	for (int i = 0; i < n_gpu_kinds; ++i)
+		if (gpu_kinds[i] == destroy) return;
+	if (n_gpu_kinds < (int) LENGTH(gpu_kinds)) gpu_kinds[n_gpu_kinds++] = destroy;
+}
+
+int gpu_effect_is(const struct effect *e)
+{
+	if (!e || !e->data || !e->destroy) return 0;
+	for (int i = 0; i < n_gpu_kinds; ++i)
+		if (gpu_kinds[i] == e->destroy) return 1;
+	return 0;
+}
+
+static sample_t * gpu_passenger_run(struct effect *e, ssize_t *frames, sample_t *ibuf, sample_t *obuf)
+{
+	return ibuf;   /* this effect's operators already ran inside the device chain of the head of its run */
+}
+
+void gpu_link_neighbours(struct effect *e)
+{
+	struct gpu_effect_state *st = (struct gpu_effect_state *) e->data;
+	if (st->link_checked) return;
+	st->link_checked = 1;
+	if (!st->head && !getenv("DSP_B200_NO_LINK")) {
+		for (struct effect *n = e->next; gpu_effect_is(n); n = n->next) {
+			struct gpu_effect_state *ns = (struct gpu_effect_state *) n->data;
+			if (ns->head || !ns->chain || n->istream.channels != e->istream.channels) break;
+			if (dspb200_chain_absorb(st->chain, ns->chain) != 0) break;
+			LOG_FMT(LL_VERBOSE, "%s: info: device chain continues through %s (no host copy in between)", e->name, n->name);
+			ns->head = st;
+			ns->link_checked = 1;
+			n->run = gpu_passenger_run;
+		}
+	}
+	st->inplace = dspb200_chain_inplace_ok(st->chain);
+}
+
+/* run() of the head of a run of GPU effects (and of every GPU effect that stands alone) */
+sample_t * gpu_linked_run(struct effect *e, ssize_t *frames, sample_t *ibuf, sample_t *obuf)
 {
 	struct gpu_effect_state *state = (struct gpu_effect_state *) e->data;
-	const long r = dspb200_chain_run_host(state->chain, *frames, ibuf, ibuf);
-	if (r < 0 && !state->failed) {
-		/* run() has no error channel: say so once, keep the audio flowing */
-		state->failed = 1;
-		LOG_FMT(LL_ERROR, "%s: error: device run failed, passing audio through: %s", e->name, dspb200_last_error());
+	gpu_link_neighbours(e);
+	sample_t *dst = (state->inplace) ? ibuf : obuf;
+	const long r = dspb200_chain_run_host(state->chain, *frames, ibuf, dst);
+	if (r < 0) {
+		if (!state->failed) {
+			/* run() has no error channel: say so once; the block's content is whatever the copies left */
+			state->failed = 1;
+			LOG_FMT(LL_ERROR, "%s: error: device run failed, this block is not processed: %s", e->name, dspb200_last_error());
+		}
+		if (!state->inplace) *frames = 0;
+		return dst;
 	}
-	return ibuf;
+	*frames = r;
+	return dst;
 }
 
 static void gpu_effect_reset(struct effect *e)
 {
 	struct gpu_effect_state *state = (struct gpu_effect_state *) e->data;
+	if (state->head) return;   /* the head of the run resets the whole device chain */
 	dspb200_chain_reset(state->chain);
 }
 
@@ -206,7 +258,8 @@ struct effect * gpu_effect_new(const struct effect_info *ei, const struct stream
 	e->istream.channels = e->ostream.channels = istream->channels;
 	e->flags |= EFFECT_FLAG_OPT_REORDERABLE;
 	e->flags |= EFFECT_FLAG_CH_DEPS_IDENTITY;
-	e->run = gpu_effect_run;
+	gpu_register_effect_kind(gpu_effect_destroy);
+	e->run = gpu_linked_run;
 	e->reset = gpu_effect_reset;
 	e->plot = gpu_effect_plot;
 	e->destroy = gpu_effect_destroy;

@@ -15,29 +15,18 @@
 #include "util.h"
 #include "gpu_effect.h"
 
-static sample_t * gpu_resample_run(struct effect *e, ssize_t *frames, sample_t *ibuf, sample_t *obuf)
-{
-	struct gpu_effect_state *state = (struct gpu_effect_state *) e->data;
-	const long r = dspb200_chain_run_host(state->chain, *frames, ibuf, obuf);
-	if (r < 0) {
-		if (!state->failed) LOG_FMT(LL_ERROR, "%s: error: device run failed: %s", e->name, dspb200_last_error());
-		state->failed = 1;
-		*frames = 0;
-		return obuf;
-	}
-	*frames = r;
-	return obuf;
-}
-
 static void gpu_resample_reset(struct effect *e)
 {
-	dspb200_chain_reset(((struct gpu_effect_state *) e->data)->chain);
+	struct gpu_effect_state *state = (struct gpu_effect_state *) e->data;
+	if (state->head) return;   /* a passenger: the head of the run resets the whole device chain */
+	dspb200_chain_reset(state->chain);
 }
 
 static sample_t * gpu_resample_drain2(struct effect *e, ssize_t *frames, sample_t *buf1, sample_t *buf2)
 {
 	struct gpu_effect_state *state = (struct gpu_effect_state *) e->data;
-	const long r = dspb200_chain_drain_host(state->chain, *frames, buf2);
+	/* as a passenger the resampler lives in the head's device chain: drain that one (it runs what follows, too) */
+	const long r = dspb200_chain_drain_host(state->head ? state->head->chain : state->chain, *frames, buf2);
 	if (r < 0) {
 		*frames = -1;
 		return buf1;
@@ -113,7 +102,8 @@ struct effect * resample_effect_init(const struct effect_info *ei, const struct 
 	e->ostream.fs = rate;
 	e->istream.channels = e->ostream.channels = istream->channels;
 	e->flags |= EFFECT_FLAG_CH_DEPS_IDENTITY;
-	e->run = gpu_resample_run;
+	gpu_register_effect_kind(gpu_resample_destroy);
+	e->run = gpu_linked_run;   /* out of place: the chain holds a rate-changing operator */
 	e->reset = gpu_resample_reset;
 	e->drain2 = gpu_resample_drain2;
 	e->destroy = gpu_resample_destroy;

@@ -54,6 +54,10 @@ def main():
     save("fir_align_end", ":1 fir -a-100S -t pcm -e double -c 1 -r 48000 ir700.f64", 48000, 3, 512, x)
     save("hilbert_c", ":0 hilbert -c 255", 48000, 3, 333, x)
     save("hilbert_pc", ":0,1 hilbert -p -c 255 :2 eq 1k 1.0 3", 48000, 3, 333, x)
+    # reverse IIR (biquad -r, reverse_iir.c): the linear-phase LR4 crossover of examples/crossover_lr4_2kHz_riir_linphase
+    # without its remix (4 channels in), two -r sections per band merged by the chain, plus a lone -r section
+    x4 = np.concatenate([x, x[:, :1] * 0.5], axis=1)
+    save("riir", ":0,1 highpass 2k bw2 highpass -r 2k bw2 : :2,3 lowpass 2k bw2 lowpass -r 2k bw2 : :1 eq -r 500 1.0 4", 48000, 4, 500, x4)
     # resample both ways, ragged blocks, drain included
     x = ref.sgen("sine:freq=1k+3000S", 44100, 2, 3000) * 0.8
     x[:, 1] = rng.standard_normal(3000) * 0.3

@@ -23,7 +23,9 @@ RMS_TOL = 1e-10
 NAMES = ["gain", "biquad", "fir_p", "fir_p_2ch", "fir", "fir_direct", "hilbert", "resample_up", "resample_down",
          "resample_2x", "chain",
          # -a / -c alignment: fir_get_offset -> ref -> channel_offsets -> the reference's align pass (effects_chain.c:744-864)
-         "fir_p_align", "fir_align_end", "hilbert_c", "hilbert_pc"]
+         "fir_p_align", "fir_align_end", "hilbert_c", "hilbert_pc",
+         # biquad -r: the reference's reverse-IIR design, run as a device FIR (shim/riir.c)
+         "riir"]
 LADSPA = os.path.join(HERE, "dropin", "_build", "ladspa_dsp_b200.so")
 
 
@@ -269,3 +271,57 @@ def test_ladspa_frontend_runs_gpu_chain(dropin, have_ref, tmp_path):
         r.close()
         assert got.shape == want.shape
         assert rms(got - want.astype(np.float32).astype(np.float64)) <= 1e-7      # float32 ports
+
+
+def test_device_chain_continues_across_align_and_resample(dropin, gpu_lib, have_ref):
+    """runs of GPU effects the optimizer cannot merge -- a latency-bearing `fir`, the chain's `align`
+    (now a device operator), `biquad -r`, `resample` -- are still one device chain per block: ONE host->device and ONE
+    device->host copy per run_effects_chain() call (copy counter of the library), output equal to the reference's."""
+    ir = os.path.join(GOLDEN, "ir700.f64")
+    cases = [
+        # (chain, fs, channels, block): config 5 in miniature; fir's FFT path (latency 700 -> align discards 700 frames)
+        # between two biquads and a resampler; reverse IIR + alignment of the other channel + resample
+        ("eq 100 1.0 2 eq 1k 1.0 -2 eq 5k 2.0 1 fir_p -t pcm -e double -c 1 -r 44100 %s resample 48k" % ir, 44100, 2, 512),
+        ("eq 200 1.0 3 fir -t pcm -e double -c 1 -r 44100 %s eq 3k 1.0 -3 resample 48k" % ir, 44100, 2, 500),
+        (":0 highpass -r 2k bw2 : eq 300 1.0 2 resample 44100", 48000, 2, 700),
+    ]
+    rng = np.random.default_rng(21)
+    for chain, fs, C, block in cases:
+        x = rng.standard_normal((9 * block, C)) * 0.2
+        g = dropin.RefChain(chain, fs, C, lib_path=DROPIN)
+        names = g.effect_names()
+        outs, counts = [], []
+        for i in range(0, x.shape[0], block):
+            h0, d0 = gpu_lib.copy_counts()
+            y = g.run(x[i:i + block])
+            h1, d1 = gpu_lib.copy_counts()
+            assert (h1 - h0, d1 - d0) == (1, 1), (chain, names, h1 - h0, d1 - d0)
+            outs.append(y)
+            counts.append(y.shape[0])
+        for y in g.drain(block):
+            outs.append(y)
+            counts.append(y.shape[0])
+        g.close()
+        got = np.concatenate(outs)
+        if have_ref:
+            r = dropin.RefChain(chain, fs, C)
+            want, wcounts = r.process(x, block)
+            r.close()
+            assert counts == list(wcounts), (chain, counts[:6], list(wcounts)[:6])
+            assert got.shape == want.shape
+            assert rms(got - want) <= RMS_TOL, (chain, rms(got - want))
+    # and with the hand-off disabled the same chains still agree (every effect on its own device chain)
+    os.environ["DSP_B200_NO_LINK"] = "1"
+    try:
+        chain, fs, C, block = cases[1]
+        x = rng.standard_normal((6 * block, C)) * 0.2
+        g = dropin.RefChain(chain, fs, C, lib_path=DROPIN)
+        got, counts = g.process(x, block)
+        g.close()
+        if have_ref:
+            r = dropin.RefChain(chain, fs, C)
+            want, wcounts = r.process(x, block)
+            r.close()
+            assert counts == list(wcounts) and rms(got - want) <= RMS_TOL
+    finally:
+        os.environ.pop("DSP_B200_NO_LINK", None)

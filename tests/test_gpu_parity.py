@@ -441,3 +441,28 @@ def test_full_size_config5_chain_share(gpu_lib, have_ref):
         assert rms(got[:, :4] - want) <= RMS_TOL
         assert np.array_equal(got, np.tile(got[:, :4], (1, C // 4)))
     ch.close()
+
+
+def test_align_operator_delays_and_discard(gpu_lib):
+    """Device `align` (align.c:35-64): per-channel whole-frame delays through rings that persist across calls of any
+    size, the first `discard` frames of the stream dropped (a call returns the tail of its block)."""
+    fs, C = 48000, 6
+    delays = [0, 3, 700, 1, 0, 5000]
+    rng = np.random.default_rng(4)
+    N = 12000
+    x = rng.standard_normal((N, C))
+    for discard in (0, 1300):
+        want = np.zeros((N, C))
+        for k, d in enumerate(delays):
+            want[d:, k] = x[:N - d, k]
+        want = want[discard:]
+        ch = gpu_lib.Chain(fs, C).add_align(delays, discard)
+        cuts = [0, 1, 2, 500, 1299, 1300, 1301, 4000, 4001, 9000, N]
+        outs = [ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])]
+        got = np.concatenate(outs)
+        assert got.shape == want.shape, (discard, got.shape, want.shape)
+        assert np.array_equal(got, want)
+        ch.reset()
+        got2 = np.concatenate([ch.run(x[i:i + 4096]).copy() for i in range(0, N, 4096)])
+        assert np.array_equal(got2, want)
+        ch.close()
