@@ -1078,31 +1078,43 @@ struct FirOp : Op {
 		return buf;
 	}
 
-	~FirOp() override
+	// everything plan() made: streams, events, spectra, work buffers (the description, d_ch_map and the host taps stay)
+	void free_plan()
 	{
 		if (side) {
 			cudaStreamSynchronize(side);
 			cudaStreamDestroy(side);
+			side = nullptr;
 		}
 		if (side2) {
 			cudaStreamSynchronize(side2);
 			cudaStreamDestroy(side2);
+			side2 = nullptr;
 		}
-		for (cudaEvent_t e : ev_batch)
-			if (e) cudaEventDestroy(e);
-		for (cudaEvent_t e : ev_tail)
-			if (e) cudaEventDestroy(e);
-		for (cudaEvent_t e : ev_join)
-			if (e) cudaEventDestroy(e);
-		dev_free(d_V);
+		for (cudaEvent_t &e : ev_batch) { if (e) cudaEventDestroy(e); e = nullptr; }
+		for (cudaEvent_t &e : ev_tail) { if (e) cudaEventDestroy(e); e = nullptr; }
+		for (cudaEvent_t &e : ev_join) { if (e) cudaEventDestroy(e); e = nullptr; }
 		if (ev_main) cudaEventDestroy(ev_main);
 		if (ev_urgent) cudaEventDestroy(ev_urgent);
-		for (int l = 0; l < n_levels; ++l) lv[l].free_all();
-		dev_free(d_Y_side);
-		dev_free(d_ch_map); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
-		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp);
-		dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi);
-		dev_free(d_stats);
+		ev_main = ev_urgent = nullptr;
+		for (int l = 0; l < n_levels; ++l) {
+			lv[l].free_all();
+			lv[l] = FirLevel();
+		}
+		n_levels = 0;
+		dev_free(d_V); dev_free(d_Y_side); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
+		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp); dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi); dev_free(d_stats);
+		d_V = d_Y_side = nullptr; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
+		d_Ybulk = nullptr; d_lo = d_hi = nullptr; d_stats = nullptr;
+		ltmp_cap = 0; tail_pf = 0; t_batch = 0; use_pipe = false; pipe_pf = 0; nb_max = 1;
+		urgent_pending = false; pre_valid = false; abs_pos = 0; planned = false;
+	}
+
+	~FirOp() override
+	{
+		free_plan();
+		dev_free(d_ch_map);
+		dev_free(d_replay);
 	}
 
 	int plan(long hint, cudaStream_t st)
@@ -1238,9 +1250,7 @@ struct FirOp : Op {
 		CUDA_TRY(cudaMemcpyAsync(d_h0, h0.data(), h0.size() * sizeof(double), cudaMemcpyHostToDevice, st), return -1);
 		CUDA_TRY(cudaStreamSynchronize(st), return -1);
 		dev_free(d_taps);
-		h_taps.clear();
-		h_taps.shrink_to_fit();
-		planned = true;
+		planned = true;   // the host taps stay: a plan made from an unrepresentative first call is redone once (maybe_replan)
 		return 0;
 	}
 
@@ -1268,6 +1278,8 @@ struct FirOp : Op {
 	void reset(cudaStream_t st) override
 	{
 		abs_pos = 0; pre_valid = false; urgent_pending = false;
+		replay_frames = 0;
+		replay_open = replans < 2;
 		if (!planned) return;
 		if (side) cudaStreamSynchronize(side);
 		if (side2) cudaStreamSynchronize(side2);
@@ -1541,6 +1553,59 @@ struct FirOp : Op {
 		return 0;
 	}
 
+	// ---- re-planning ---------------------------------------------------------------------------------
+	// The partition size comes from the first call's frame count (or the caller's hint).  Frontends do not always
+	// open with a representative call (a LADSPA host probing with a few frames, a short first read): while the stream
+	// is younger than REPLAY_MAX frames its input is kept, and when a later call is at least twice the planned block
+	// the plan is redone for that size and the kept input replayed through it (outputs discarded) -- the state is then
+	// exactly what it would have been with the right plan from the start.
+	static constexpr long REPLAY_MAX = 16384;
+	double *d_replay = nullptr;      // [replay_frames][channels], interleaved as it came
+	long replay_frames = 0;
+	bool replay_open = true;
+	int replans = 0;
+
+	int keep_for_replay(long frames, const double *in, cudaStream_t st)
+	{
+		if (!replay_open) return 0;
+		if (replay_frames + frames > REPLAY_MAX || replans >= 2 || B0 >= 4096) {
+			replay_open = false;
+			dev_free(d_replay);
+			d_replay = nullptr;
+			return 0;
+		}
+		if (!d_replay) {
+			d_replay = dev_alloc<double>((size_t) REPLAY_MAX * channels, false);
+			if (!d_replay) { replay_open = false; return 0; }   // no memory to spare: keep the first plan
+		}
+		CUDA_TRY(cudaMemcpyAsync(d_replay + replay_frames * channels, in, (size_t) frames * channels * sizeof(double), cudaMemcpyDeviceToDevice, st), return -1);
+		replay_frames += frames;
+		return 0;
+	}
+
+	int maybe_replan(long frames, cudaStream_t st)
+	{
+		if (!replay_open || !planned || frames < 2L * B0 || replay_frames == 0 && abs_pos > 0) return 0;
+		if (getenv("DSP_B200_FIR_NO_REPLAN")) return 0;
+		const long kept = replay_frames;
+		CUDA_TRY(cudaStreamSynchronize(st), return -1);
+		free_plan();
+		++replans;
+		if (plan(frames, st)) return -1;
+		if (kept > 0) {
+			double *scratch = dev_alloc<double>((size_t) kept * channels, false);
+			if (!scratch) return -1;
+			const bool was_open = replay_open;
+			replay_open = false;   // the replay itself is not recorded again
+			const long r = run_planned(kept, d_replay, scratch, st);
+			replay_open = was_open;
+			CUDA_TRY(cudaStreamSynchronize(st), return -1);
+			dev_free(scratch);
+			if (r < 0) return -1;
+		}
+		return 0;
+	}
+
 	long run(long frames, const double *in, double *out, cudaStream_t st) override
 	{
 		if (frames <= 0) return 0;
@@ -1549,6 +1614,14 @@ struct FirOp : Op {
 			CUDA_TRY(cudaMemcpyAsync(out, in, (size_t) frames * C * sizeof(double), cudaMemcpyDeviceToDevice, st), return -1);
 		if (n_sel == 0) return frames;   // a slab the selector leaves empty: pass-through, nothing to plan (no taps were kept for it)
 		if (!planned && plan(frames, st)) return -1;
+		if (maybe_replan(frames, st)) return -1;
+		if (keep_for_replay(frames, in, st)) return -1;
+		return run_planned(frames, in, out, st);
+	}
+
+	long run_planned(long frames, const double *in, double *out, cudaStream_t st)
+	{
+		const long C = channels;
 
 		// where the convolution result goes: straight to `out`, or to a compact temp when a latency ring follows
 		double *dst = out;

@@ -15,7 +15,7 @@
 //                                 mbarrier) and tags every stage with a command word.  It issues the stages of (a) as
 //                                 soon as the spectrum buffer `sbuf` is free for the channel and fills all other time
 //                                 with its share of the work items of (b) -- the HBM stream never waits for a transform.
-//   MAC warps (8)                 execute the command of each stage: complex multiply-accumulate of 512 bins (2 per
+//   MAC warps (4)                 execute the command of each stage: complex multiply-accumulate of 256 bins (2 per
 //                                 lane) into registers, sums of (a) dropped into `sbuf`, sums of (b) stored to V
 //   transform team (N/16 threads) reads the caller's interleaved block, forward FFT in shared memory, spectrum to the
 //                                 FDL, S = sbuf + X_j H_0 for the bin pairs it owns, inverse FFT in place,
@@ -36,13 +36,13 @@ constexpr int PIPE_TB = 4;   // batch depth of (b): outputs per pass, = number o
 template <int N>
 struct PipeCfg {
 	static constexpr int TF = N / 16;                 // transform team (one FFT)
-	static constexpr int MAC_WARPS = 8;
+	static constexpr int MAC_WARPS = 4;               // 8 + 4 + 1 warps: at most 4 warps per SM sub-partition, 128 registers each
 	static constexpr int TM = MAC_WARPS * 32;
 	static constexpr int THREADS = TF + TM + 32;      // + producer warp
-	static constexpr int CHUNK = 512;                 // bins per stage
+	static constexpr int CHUNK = 256;                 // bins per stage
 	static constexpr int NCHUNK = N / CHUNK;
 	static constexpr int PER = CHUNK / TM;            // bins per MAC lane and stage
-	static constexpr int NS = (N >= 4096) ? 5 : 8;    // ring stages
+	static constexpr int NS = (N >= 4096) ? 10 : 16;  // ring stages (8 KB each)
 	static constexpr size_t STAGE_BYTES = 2 * (size_t) CHUNK * sizeof(double2);   // X chunk | H chunk
 	static constexpr size_t FBUF = (size_t) FftCfg<N>::STRIDE * sizeof(double2);
 	static constexpr size_t SBUF = (size_t) N * sizeof(double2);
@@ -159,9 +159,11 @@ __device__ __forceinline__ void pipe_prefetch_rows(const void *p, long bytes, in
 	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
-// Register cap: 17 warps x 32 x 112 registers = 60928 of the 65536 (registers are allocated per warp in units of 512: 120 would not fit).
+// Register cap: the register file is split over the SM's four sub-partitions (16384 each) and a CTA's warps are dealt
+// round-robin: 13 warps = at most 4 per sub-partition = 128 registers per thread (a 17-warp layout with 8 MAC warps
+// would have to fit 5 x 32 x R <= 16384, i.e. 96 registers, which the transform team cannot live with).
 #ifndef FIR_PIPE_MAXNREG
-#define FIR_PIPE_MAXNREG 112
+#define FIR_PIPE_MAXNREG 128
 #endif
 
 template <int N>

@@ -466,3 +466,27 @@ def test_align_operator_delays_and_discard(gpu_lib):
         got2 = np.concatenate([ch.run(x[i:i + 4096]).copy() for i in range(0, N, 4096)])
         assert np.array_equal(got2, want)
         ch.close()
+
+
+def test_fir_replans_after_unrepresentative_first_call(gpu_lib):
+    """A first call of 7 frames must not pin 64-frame partitions for the life of the effect: the next, representative
+    call (2048 frames) redoes the plan and replays the frames seen so far; the stream is the same as ever."""
+    from oracle import restate
+    fs, C, taps = 48000, 3, 30000
+    rng = np.random.default_rng(17)
+    h = np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
+    sizes = [7, 2048, 2048, 100, 2048, 2048, 2048, 4096, 2048]
+    x = rng.standard_normal((sum(sizes), C)) * 0.2
+    want = restate.fir_stream(x, h)
+    ch = gpu_lib.Chain(fs, C).add_fir(h)
+    outs, pos = [], 0
+    for i, n in enumerate(sizes):
+        outs.append(ch.run(x[pos:pos + n]).copy())
+        pos += n
+        if i == 0:
+            assert ch.describe()[0]["levels"][0]["B"] == 64
+        if i == 1:
+            assert ch.describe()[0]["levels"][0]["B"] == 2048, ch.describe()[0]
+    got = np.concatenate(outs)
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+    ch.close()
