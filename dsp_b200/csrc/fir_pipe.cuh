@@ -119,6 +119,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
 	return ok != 0;
 }
 
+// non-blocking probe (the MAC warps look at the NEXT stage before they work on the current one: its latency hides
+// behind the arithmetic)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, unsigned parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	             : "=r"(ok)
+	             : "r"(smem_u32(bar)), "r"(parity)
+	             : "memory");
+	return ok != 0;
+}
+
+// one lane of a converged warp (ptxas then knows the code under it is executed by a single thread: the bulk copies
+// are issued straight from uniform registers instead of a per-lane loop)
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t pred;
+	asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+	return pred != 0;
+}
+
 // try_wait suspends the warp in hardware for a bounded time; a wait that has not come true after 2^20 of them (>= 50 ms) is a
 // protocol bug: trap (the launch fails with an error) rather than hang the device
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
@@ -324,75 +345,41 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 #pragma unroll
 			for (int u = 0; u < TB; ++u) { accB[u][i] = zero; hw[u][i] = zero; }
 		}
+		{
+			const long long t0 = stats_on ? clock64() : 0;
+			mbar_wait(&full[stage], phase);
+			if (stats_on) t_wait += clock64() - t0;
+		}
+		int4 cmd = cmds[stage];
 		for (;;) {
-			{
-				const long long t0 = stats_on ? clock64() : 0;
-				mbar_wait(&full[stage], phase);
-				if (stats_on) t_wait += clock64() - t0;
-			}
-			const int4 cmd = cmds[stage];
 			const int fl = cmd.x, chunk = cmd.y, s = cmd.z;
 			if (fl & PC_EXIT) break;
+			// probe the next stage now, use the answer after this stage's arithmetic
+			int nstage = stage + 1;
+			unsigned nphase = phase;
+			if (nstage == NS) { nstage = 0; nphase ^= 1; }
+			const bool next_ready = mbar_test_wait(&full[nstage], nphase);
 			const double2 *Xs = ring + (size_t) stage * 2 * CHUNK, *Hs = Xs + CHUNK;
 			const bool dc = (chunk == 0 && tm == 0);   // bin 0 packs (DC, Nyquist): two real products
-			if (fl & (PC_SZERO | PC_SMAC | PC_SADDV | PC_SSTORE)) {
-				if (fl & PC_SZERO) {
+			if (fl & PC_BSTEP) {
 #pragma unroll
-					for (int i = 0; i < PER; ++i) accS[i] = zero;
-				}
-				if (fl & PC_SMAC) {
-					double2 x[PER], h[PER];
+				for (int i = 0; i < PER; ++i) {
+					const double2 x = Xs[tm + i * TM];
+					const double2 hn = (fl & PC_BHASH) ? Hs[tm + i * TM] : zero;
+					if (dc && i == 0) {
 #pragma unroll
-					for (int i = 0; i < PER; ++i) { x[i] = Xs[tm + i * TM]; h[i] = Hs[tm + i * TM]; }
-					if (dc) {
-						accS[0].x = fma(x[0].x, h[0].x, accS[0].x);
-						accS[0].y = fma(x[0].y, h[0].y, accS[0].y);
-					}
-					else accS[0] = pipe_cmac(accS[0], x[0], h[0]);
-#pragma unroll
-					for (int i = 1; i < PER; ++i) accS[i] = pipe_cmac(accS[i], x[i], h[i]);
-				}
-				if (fl & PC_SADDV) {
-#pragma unroll
-					for (int i = 0; i < PER; ++i) {
-						const double2 v = Xs[tm + i * TM];
-						accS[i].x += v.x; accS[i].y += v.y;
-					}
-				}
-				if (fl & PC_SSTORE) {
-#pragma unroll
-					for (int i = 0; i < PER; ++i) sbuf[chunk * CHUNK + tm + i * TM] = accS[i];
-				}
-			}
-			else {
-				if (fl & PC_BINIT) {
-#pragma unroll
-					for (int i = 0; i < PER; ++i) {
-#pragma unroll
-						for (int u = 0; u < TB; ++u) { accB[u][i] = zero; hw[u][i] = zero; }
-						if (fl & PC_BHASH) hw[TB - 1][i] = Hs[tm + i * TM];
-					}
-				}
-				if (fl & PC_BSTEP) {
-#pragma unroll
-					for (int i = 0; i < PER; ++i) {
-						const double2 x = Xs[tm + i * TM];
-						const double2 hn = (fl & PC_BHASH) ? Hs[tm + i * TM] : zero;
-						if (dc && i == 0) {
-#pragma unroll
-							for (int u = 0; u < TB; ++u) {
-								accB[u][i].x = fma(x.x, hw[u][i].x, accB[u][i].x);
-								accB[u][i].y = fma(x.y, hw[u][i].y, accB[u][i].y);
-							}
+						for (int u = 0; u < TB; ++u) {
+							accB[u][i].x = fma(x.x, hw[u][i].x, accB[u][i].x);
+							accB[u][i].y = fma(x.y, hw[u][i].y, accB[u][i].y);
 						}
-						else {
-#pragma unroll
-							for (int u = 0; u < TB; ++u) accB[u][i] = pipe_cmac(accB[u][i], x, hw[u][i]);
-						}
-#pragma unroll
-						for (int u = 0; u + 1 < TB; ++u) hw[u][i] = hw[u + 1][i];
-						hw[TB - 1][i] = hn;
 					}
+					else {
+#pragma unroll
+						for (int u = 0; u < TB; ++u) accB[u][i] = pipe_cmac(accB[u][i], x, hw[u][i]);
+					}
+#pragma unroll
+					for (int u = 0; u + 1 < TB; ++u) hw[u][i] = hw[u + 1][i];
+					hw[TB - 1][i] = hn;
 				}
 				if (fl & PC_BSTORE) {
 #pragma unroll
@@ -404,21 +391,71 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 					}
 				}
 			}
+			else if (fl & PC_SMAC) {
+				double2 x[PER], h[PER];
+#pragma unroll
+				for (int i = 0; i < PER; ++i) { x[i] = Xs[tm + i * TM]; h[i] = Hs[tm + i * TM]; }
+				if (fl & PC_SZERO) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) accS[i] = zero;
+				}
+				if (dc) {
+					accS[0].x = fma(x[0].x, h[0].x, accS[0].x);
+					accS[0].y = fma(x[0].y, h[0].y, accS[0].y);
+				}
+				else accS[0] = pipe_cmac(accS[0], x[0], h[0]);
+#pragma unroll
+				for (int i = 1; i < PER; ++i) accS[i] = pipe_cmac(accS[i], x[i], h[i]);
+				if (fl & PC_SSTORE) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) sbuf[chunk * CHUNK + tm + i * TM] = accS[i];
+				}
+			}
+			else if (fl & (PC_SADDV | PC_SSTORE)) {
+				if (fl & PC_SZERO) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) accS[i] = zero;
+				}
+				if (fl & PC_SADDV) {
+#pragma unroll
+					for (int i = 0; i < PER; ++i) {
+						const double2 v = Xs[tm + i * TM];
+						accS[i].x += v.x; accS[i].y += v.y;
+					}
+				}
+#pragma unroll
+				for (int i = 0; i < PER; ++i) sbuf[chunk * CHUNK + tm + i * TM] = accS[i];
+			}
+			else if (fl & PC_BINIT) {
+#pragma unroll
+				for (int i = 0; i < PER; ++i) {
+#pragma unroll
+					for (int u = 0; u < TB; ++u) { accB[u][i] = zero; hw[u][i] = zero; }
+					if (fl & PC_BHASH) hw[TB - 1][i] = Hs[tm + i * TM];
+				}
+			}
 			__syncwarp();
 			if (lane == 0) {
 				if (fl & PC_SFULL) mbar_arrive(s_full);   // after this warp's part of the last chunk is in sbuf
 				mbar_arrive(&empty[stage]);
 			}
-			if (++stage == NS) { stage = 0; phase ^= 1; }
+			if (!next_ready) {
+				const long long t0 = stats_on ? clock64() : 0;
+				mbar_wait(&full[nstage], nphase);
+				if (stats_on) t_wait += clock64() - t0;
+			}
+			stage = nstage;
+			phase = nphase;
+			cmd = cmds[stage];
 		}
 		if (stats_on && tm == 0) {
 			a.stats[blockIdx.x * 8 + 1] = t_wait;
 			a.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
 		}
 	}
-	else if (lane == 0) {
+	else if (elect_one()) {
 		// ------------------------------------------------------------------------------------------
-		// producer / scheduler
+		// producer / scheduler (one elected lane of the last warp)
 		// ------------------------------------------------------------------------------------------
 		const uint64_t pol = l2_policy_evict_first();
 		const bool hint_x = a.evict_first != 0, hint_h = a.evict_first != 0 && a.h_ch_stride != 0;
@@ -480,15 +517,15 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			// window[t] = H_{3+t} where it belongs to the batch (p >= pf): with pf = TB + 2 only t = TB-1 does
 			const int p0 = a.pf;
 			emit(PC_BINIT | ((p0 < a.P) ? PC_BHASH : 0), c, s, nullptr, (p0 < a.P) ? Hc + (long) p0 * N : nullptr, false, hint_h);
-			// step m: X_{j+2-m} (row slot-1-(m-3)... relative to this block's row) meets window; next window row H_{m+TB}
+			// step m: X_{j+2-m} (one row further back per step, starting at block j-1) meets the window; next window row H_{m+TB}
+			int sl = a.slot - 1;
+			if (sl < 0) sl += a.fdl_rows;
+			const double2 *hp = Hc + (long) (3 + TB) * N;
 			for (int m = 3; m < a.P; ++m) {
-				int sl = a.slot - (m - 2);              // row of block j - (m - 2) = (j - 1) + 3 - m
-				sl %= a.fdl_rows;
-				if (sl < 0) sl += a.fdl_rows;
-				const int hn = m + TB;
-				const bool hh = hn < a.P;
-				emit(PC_BSTEP | (hh ? PC_BHASH : 0) | ((m == a.P - 1) ? PC_BSTORE : 0), c, s, fdl + (long) sl * N,
-				     hh ? Hc + (long) hn * N : nullptr, hint_x, hint_h);
+				const bool hh = m + TB < a.P;
+				emit(PC_BSTEP | (hh ? PC_BHASH : 0) | ((m == a.P - 1) ? PC_BSTORE : 0), c, s, fdl + (long) sl * N, hh ? hp : nullptr, hint_x, hint_h);
+				hp += N;
+				if (--sl < 0) sl += a.fdl_rows;
 			}
 		};
 

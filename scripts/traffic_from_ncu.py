@@ -7,7 +7,7 @@ kernel, times its launches per step as counted in the same capture window.
 """
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep = os.path.join(ROOT, "gpurun_out", "prof_fir_step.ncu-rep")
+rep = os.path.join(ROOT, "gpurun_out", os.environ.get("NCU_REP", "prof_fir_step.ncu-rep"))
 C, F, taps, h = (int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (256, 4096, 131072, 1)))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -20,7 +20,8 @@ for r in rows[2:]:
     name = r[ki].split("(")[0].replace("void ", "").replace("dspb200::", "")
     b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
     per.setdefault(name, []).append((b, float(r[ti])))
-n_l0 = sum(len(v) for k, v in per.items() if k.startswith("k_fir_level0"))   # one fused level-0 launch per step
+pipe = any(k.startswith("k_fir_pipe") for k in per)
+n_l0 = sum(len(v) for k, v in per.items() if k.startswith("k_fir_pipe" if pipe else "k_fir_level0"))   # one block kernel launch per step
 out = {"kernels": {}, "window_steps": n_l0}
 total = 0.0
 for k, v in per.items():
@@ -32,6 +33,6 @@ out["dram_bytes_per_step"] = total
 out["source"] = "ncu --set full --clock-control none -k regex:k_fir_ (gpurun_out/prof_fir_step.ncu-rep); dram__bytes_read.sum + dram__bytes_write.sum"
 path = os.path.join(ROOT, "profiles", "traffic.json")
 tr = json.load(open(path)) if os.path.exists(path) else {}
-tr["step:C%d:F%d:taps%d:h%d" % (C, F, taps, h)] = out
+tr["step:C%d:F%d:taps%d:h%d:pipe%d" % (C, F, taps, h, 1 if pipe else 0)] = out
 json.dump(tr, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))

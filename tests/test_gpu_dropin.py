@@ -295,7 +295,8 @@ def test_device_chain_continues_across_align_and_resample(dropin, gpu_lib, have_
             h0, d0 = gpu_lib.copy_counts()
             y = g.run(x[i:i + block])
             h1, d1 = gpu_lib.copy_counts()
-            assert (h1 - h0, d1 - d0) == (1, 1), (chain, names, h1 - h0, d1 - d0)
+            # (a call that yields no frames yet -- the resampler still filling its first block -- has nothing to copy back)
+            assert (h1 - h0, d1 - d0) == (1, 1 if y.shape[0] > 0 else 0), (chain, names, h1 - h0, d1 - d0)
             outs.append(y)
             counts.append(y.shape[0])
         for y in g.drain(block):
