@@ -42,8 +42,9 @@ struct PipeCfg {
 	static constexpr int CHUNK = 256;                 // bins per stage
 	static constexpr int NCHUNK = N / CHUNK;
 	static constexpr int PER = CHUNK / TM;            // bins per MAC lane and stage
-	static constexpr int NS = (N >= 4096) ? 10 : 16;  // ring stages (8 KB each)
-	static constexpr size_t STAGE_BYTES = 2 * (size_t) CHUNK * sizeof(double2);   // X chunk | H chunk
+	static constexpr int SLOTS = 2;                   // (X chunk | H chunk) pairs per stage: one barrier round trip per two rows
+	static constexpr int NS = (N >= 4096) ? 5 : 8;    // ring stages (16 KB each)
+	static constexpr size_t STAGE_BYTES = SLOTS * 2 * (size_t) CHUNK * sizeof(double2);
 	static constexpr size_t FBUF = (size_t) FftCfg<N>::STRIDE * sizeof(double2);
 	static constexpr size_t SBUF = (size_t) N * sizeof(double2);
 	static constexpr size_t CMDS = (size_t) NS * sizeof(int4);
@@ -352,15 +353,14 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		}
 		int4 cmd = cmds[stage];
 		for (;;) {
-			const int fl = cmd.x, chunk = cmd.y, s = cmd.z;
-			if (fl & PC_EXIT) break;
-			// probe the next stage now, use the answer after this stage's arithmetic
-			int nstage = stage + 1;
-			unsigned nphase = phase;
-			if (nstage == NS) { nstage = 0; nphase ^= 1; }
-			const bool next_ready = mbar_test_wait(&full[nstage], nphase);
-			const double2 *Xs = ring + (size_t) stage * 2 * CHUNK, *Hs = Xs + CHUNK;
+			const int flw = cmd.x, chunk = cmd.y, s = cmd.z;
+			if (flw & PC_EXIT) break;
 			const bool dc = (chunk == 0 && tm == 0);   // bin 0 packs (DC, Nyquist): two real products
+#pragma unroll
+			for (int sl_ = 0; sl_ < Cfg::SLOTS; ++sl_) {
+			const int fl = (sl_ == 0) ? (flw & 0xffff) : (flw >> 16);
+			if (sl_ > 0 && fl == 0) break;
+			const double2 *Xs = ring + ((size_t) stage * Cfg::SLOTS + sl_) * 2 * CHUNK, *Hs = Xs + CHUNK;
 			if (fl & PC_BSTEP) {
 #pragma unroll
 				for (int i = 0; i < PER; ++i) {
@@ -434,18 +434,22 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 					if (fl & PC_BHASH) hw[TB - 1][i] = Hs[tm + i * TM];
 				}
 			}
+			}
 			__syncwarp();
 			if (lane == 0) {
-				if (fl & PC_SFULL) mbar_arrive(s_full);   // after this warp's part of the last chunk is in sbuf
+				if ((flw | (flw >> 16)) & PC_SFULL) mbar_arrive(s_full);   // after this warp's part of the last chunk is in sbuf
 				mbar_arrive(&empty[stage]);
 			}
-			if (!next_ready) {
+			// (a warp issues in order: probing the next stage's barrier ahead of the arithmetic would only stall the
+			// arithmetic behind the probe's answer -- so the wait comes here, once per two rows)
+			const bool wrap = (stage + 1 == NS);
+			stage = wrap ? 0 : stage + 1;
+			phase ^= wrap ? 1u : 0u;
+			{
 				const long long t0 = stats_on ? clock64() : 0;
-				mbar_wait(&full[nstage], nphase);
+				mbar_wait(&full[stage], phase);
 				if (stats_on) t_wait += clock64() - t0;
 			}
-			stage = nstage;
-			phase = nphase;
 			cmd = cmds[stage];
 		}
 		if (stats_on && tm == 0) {
@@ -468,22 +472,38 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		unsigned phase = 0;
 		long n_stages = 0;
 
-		// one stage: wait for the slot, tag it, start the copies
-		auto emit = [&](int flags, int chunk, int s, const double2 *xsrc, const double2 *hsrc, bool hx, bool hh) {
+		// Stages carry up to SLOTS (X chunk | H chunk) pairs of one chunk of one channel: entries are collected with
+		// emit() and leave with flush() -- wait for the ring slot, tag it, start the copies.
+		static_assert(Cfg::SLOTS == 2, "the pending stage is kept in scalars");
+		int pn = 0, p_chunk = 0, p_s = 0, p_fl0 = 0, p_fl1 = 0;
+		const double2 *p_x0 = nullptr, *p_h0 = nullptr, *p_x1 = nullptr, *p_h1 = nullptr;
+		bool p_hx0 = false, p_hh0 = false, p_hx1 = false, p_hh1 = false;
+		auto flush = [&]() {
+			if (pn == 0) return;
 			{
 				const long long t0 = stats_on ? clock64() : 0;
 				mbar_wait(&empty[stage], phase ^ 1);
 				if (stats_on) t_wait += clock64() - t0;
 			}
-			cmds[stage] = make_int4(flags, chunk, s, 0);
-			double2 *dst = ring + (size_t) stage * 2 * CHUNK;
-			const unsigned bytes = (xsrc ? ROW_BYTES : 0) + (hsrc ? ROW_BYTES : 0);
+			if (pn < 2) { p_fl1 = 0; p_x1 = nullptr; p_h1 = nullptr; }
+			const unsigned bytes = (p_x0 ? ROW_BYTES : 0) + (p_h0 ? ROW_BYTES : 0) + (p_x1 ? ROW_BYTES : 0) + (p_h1 ? ROW_BYTES : 0);
+			cmds[stage] = make_int4(p_fl0 | (p_fl1 << 16), p_chunk, p_s, 0);
 			if (bytes) mbar_arrive_expect_tx(&full[stage], bytes);
-			else mbar_arrive(&full[stage]);   // nothing to copy (exit, or a row that does not exist)
-			if (xsrc) bulk_g2s(dst, xsrc, ROW_BYTES, &full[stage], hx, pol);
-			if (hsrc) bulk_g2s(dst + CHUNK, hsrc, ROW_BYTES, &full[stage], hh, pol);
+			else mbar_arrive(&full[stage]);   // nothing to copy (exit, or rows that do not exist)
+			double2 *dst = ring + (size_t) stage * Cfg::SLOTS * 2 * CHUNK;
+			if (p_x0) bulk_g2s(dst, p_x0, ROW_BYTES, &full[stage], p_hx0, pol);
+			if (p_h0) bulk_g2s(dst + CHUNK, p_h0, ROW_BYTES, &full[stage], p_hh0, pol);
+			if (p_x1) bulk_g2s(dst + 2 * CHUNK, p_x1, ROW_BYTES, &full[stage], p_hx1, pol);
+			if (p_h1) bulk_g2s(dst + 3 * CHUNK, p_h1, ROW_BYTES, &full[stage], p_hh1, pol);
 			if (++stage == NS) { stage = 0; phase ^= 1; }
 			++n_stages;
+			pn = 0;
+		};
+		auto emit = [&](int flags, int chunk, int s, const double2 *xsrc, const double2 *hsrc, bool hx, bool hh) {
+			if (pn == 0) { p_fl0 = flags; p_x0 = xsrc; p_h0 = hsrc; p_hx0 = hx; p_hh0 = hh; }
+			else { p_fl1 = flags; p_x1 = xsrc; p_h1 = hsrc; p_hx1 = hx; p_hh1 = hh; }
+			p_chunk = chunk; p_s = s;
+			if (++pn == 2) flush();
 		};
 
 		// (b): the channels s = g + TB k of this block's residue g, cut into NCHUNK items each; this CTA's share
@@ -493,7 +513,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		const int n_g = (a.V && a.blk >= 1 && a.n_ch > g && !a.no_batch_items) ? (a.n_ch - g + TB - 1) / TB : 0;
 		if (n_g > 0) {
 			const long n_items = (long) n_g * NCHUNK;
-			const long Ss = (long) NCHUNK * (a.pf - 1 + (has_v ? 1 : 0)), Sb = a.P - 2;
+			const long Ss = (long) NCHUNK * ((a.pf - 1 + (has_v ? 1 : 0) + Cfg::SLOTS - 1) / Cfg::SLOTS), Sb = (a.P - 2 + Cfg::SLOTS - 1) / Cfg::SLOTS;
 			const long total = (long) a.n_ch * Ss + n_items * Sb;
 			const long target = (total + G - 1) / G;
 			long W = 0, Wb = 0, wb = 0;
@@ -527,6 +547,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 				hp += N;
 				if (--sl < 0) sl += a.fdl_rows;
 			}
+			flush();
 		};
 
 		auto emit_channel = [&](int s) {
@@ -535,7 +556,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			const double2 *Vc = has_v ? a.V + ((a.blk % a.v_slots) * a.n_ch + s) * (long) N : nullptr;
 			for (int c = 0; c < NCHUNK; ++c) {
 				const int last = (c == NCHUNK - 1) ? PC_SFULL : 0;
-				if (a.pf <= 1 && !Vc) { emit(PC_SZERO | PC_SSTORE | last, c, s, nullptr, nullptr, false, false); continue; }
+				if (a.pf <= 1 && !Vc) { emit(PC_SZERO | PC_SSTORE | last, c, s, nullptr, nullptr, false, false); flush(); continue; }
 				for (int p = 1; p < a.pf; ++p) {
 					int sl = a.slot - p;
 					if (sl < 0) sl += a.fdl_rows;
@@ -544,6 +565,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 					emit(fl, c, s, fdl + (long) sl * N + c * CHUNK, Hc + (long) p * N + c * CHUNK, hint_x, hint_h);
 				}
 				if (Vc) emit(PC_SADDV | PC_SSTORE | last | (a.pf <= 1 ? PC_SZERO : 0), c, s, Vc + c * CHUNK, nullptr, hint_x, false);
+				flush();   // a stage never mixes chunks
 			}
 		};
 
@@ -562,6 +584,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			else break;
 		}
 		emit(PC_EXIT, 0, 0, nullptr, nullptr, false, false);
+		flush();
 		if (stats_on) {
 			a.stats[blockIdx.x * 8 + 2] = t_wait;
 			a.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;

@@ -33,6 +33,7 @@ dspb200_chain * gpu_chain_new(const char *name, const struct stream_info *istrea
 	}
 	env = getenv("DSP_B200_SLABS");
 	if (env) slabs = atoi(env);
+	else slabs = (istream->channels >= 128) ? 4 : (istream->channels >= 32) ? 2 : 1;   /* wide blocks: copy-in, kernels and copy-out of the channel slabs overlap */
 	dspb200_chain *chain = dspb200_chain_create(istream->fs, istream->channels, (n_devices) ? devices : NULL, n_devices, slabs);
 	if (!chain) LOG_FMT(LL_ERROR, "%s: error: %s", name, dspb200_last_error());
 	return chain;
