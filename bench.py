@@ -432,7 +432,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel (serialised) timing pass")
-    ap.add_argument("--e2e-slabs", type=int, default=4)
+    ap.add_argument("--e2e-slabs", type=int, default=4, help="channel slabs of the synchronous host call (copy-in / kernels / copy-out of the slabs overlap)")
+    ap.add_argument("--e2e-pipe-slabs", type=int, default=0, help="channel slabs with blocks in flight (0: same as --e2e-slabs)")
     a = ap.parse_args()
 
     # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under
@@ -589,6 +590,10 @@ def main():
                "numa": numa, "checksum": float(np.abs(pout.array).sum())}
         # the same blocks through submit/wait: up to `depth` blocks in flight, each with its own output buffer
         depth = 3
+        pslabs = a.e2e_pipe_slabs or a.e2e_slabs
+        if pslabs != a.e2e_slabs:
+            ch2.close()
+            ch2 = dsp_b200.Chain(FS, C, devices=[local_rank], slabs_per_device=pslabs).add_fir(irs, block_hint=F)
         pouts = [dsp_b200.PinnedArray((F, C)) for _ in range(depth + 1)]
         tickets, t_submit, acc = [], 0.0, 0.0
         for i in range(warm):
@@ -610,7 +615,7 @@ def main():
         barrier()
         dtp = reduce_max(dtp)
         e2e["pipelined"] = {"value": total_samples / dtp / 1e6, "unit": UNIT, "ms_per_step": dtp / steps * 1e3,
-                            "host_submit_ms_per_step": t_submit / steps * 1e3, "blocks_in_flight": depth,
+                            "host_submit_ms_per_step": t_submit / steps * 1e3, "blocks_in_flight": depth, "channel_slabs": pslabs,
                             "api": "dspb200_chain_submit_host + dspb200_chain_wait (same copies, same kernels; the synchronous call above is what the drop-in effect->run() uses)",
                             "checksum": float(np.abs(pouts[(steps - 1) % (depth + 1)].array).sum())}
         ch2.close()
