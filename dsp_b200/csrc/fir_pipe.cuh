@@ -15,7 +15,7 @@
 //                                 mbarrier) and tags every stage with a command word.  It issues the stages of (a) as
 //                                 soon as the spectrum buffer `sbuf` is free for the channel and fills all other time
 //                                 with its share of the work items of (b) -- the HBM stream never waits for a transform.
-//   MAC warps (4)                 execute the command of each stage: complex multiply-accumulate of 256 bins (2 per
+//   MAC warps (8)                 execute the command of each stage: complex multiply-accumulate of 512 bins (2 per
 //                                 lane) into registers, sums of (a) dropped into `sbuf`, sums of (b) stored to V
 //   transform team (N/16 threads) reads the caller's interleaved block, forward FFT in shared memory, spectrum to the
 //                                 FDL, S = sbuf + X_j H_0 for the bin pairs it owns, inverse FFT in place,
@@ -39,10 +39,10 @@ struct PipeCfg {
 	static constexpr int MAC_WARPS = 8;               // one bin per lane and row pair: 2 MAC warps per scheduler hide each other's latencies
 	static constexpr int TM = MAC_WARPS * 32;
 	static constexpr int THREADS = TF + TM + 128;     // + the producer's warpgroup (register reallocation works on groups of 4 warps)
-	static constexpr int CHUNK = 256;                 // bins per stage
+	static constexpr int CHUNK = 512;                 // bins per row chunk: 8 KB per bulk copy (a copy costs the issuing thread ~220 cycles whatever its size)
 	static constexpr int NCHUNK = N / CHUNK;
 	static constexpr int PER = CHUNK / TM;            // bins per MAC lane and stage
-	static constexpr int SLOTS = 2;                   // (X chunk | H chunk) pairs per stage: one barrier round trip per two rows
+	static constexpr int SLOTS = 1;                   // (X chunk | H chunk) pairs per stage
 	static constexpr int NS = (N >= 4096) ? 5 : 8;    // ring stages (16 KB each)
 	static constexpr size_t STAGE_BYTES = SLOTS * 2 * (size_t) CHUNK * sizeof(double2);
 	static constexpr size_t FBUF = (size_t) FftCfg<N>::STRIDE * sizeof(double2);
@@ -337,7 +337,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		// ------------------------------------------------------------------------------------------
 		// MAC warps: execute the stages' commands
 		// ------------------------------------------------------------------------------------------
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
 		const int tm = threadIdx.x - T;
 		int stage = 0;
 		unsigned phase = 0;
@@ -480,7 +480,7 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		// One stage = up to two (X chunk | H chunk) row pairs of one chunk of one channel: wait for the ring slot, tag
 		// it, start the copies.  (This thread runs alone: every instruction costs its full latency, so the path is
 		// kept short -- no pending state, pointers advanced by the callers.)
-		static_assert(Cfg::SLOTS == 2, "stage2() fills two row pairs");
+		static_assert(Cfg::SLOTS == 1 || Cfg::SLOTS == 2, "stage2() fills one or two row pairs");
 		auto stage2 = [&](int fl0, const double2 *x0, const double2 *h0, int fl1, const double2 *x1, const double2 *h1, int chunk, int s) {
 			{
 				const long long t0 = stats_on ? clock64() : 0;
@@ -494,8 +494,10 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			double2 *dst = ring + (size_t) stage * Cfg::SLOTS * 2 * CHUNK;
 			if (x0) bulk_g2s(dst, x0, ROW_BYTES, &full[stage], hint_x, pol);
 			if (h0) bulk_g2s(dst + CHUNK, h0, ROW_BYTES, &full[stage], hint_h, pol);
-			if (x1) bulk_g2s(dst + 2 * CHUNK, x1, ROW_BYTES, &full[stage], hint_x, pol);
-			if (h1) bulk_g2s(dst + 3 * CHUNK, h1, ROW_BYTES, &full[stage], hint_h, pol);
+			if (Cfg::SLOTS > 1) {
+				if (x1) bulk_g2s(dst + 2 * CHUNK, x1, ROW_BYTES, &full[stage], hint_x, pol);
+				if (h1) bulk_g2s(dst + 3 * CHUNK, h1, ROW_BYTES, &full[stage], hint_h, pol);
+			}
 			if (++stage == NS) { stage = 0; phase ^= 1; }
 			++n_stages;
 		};
@@ -537,11 +539,11 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			const double2 *hp = Hc + (long) (3 + TB) * N;   // H_{m+TB} for m = 3
 			int fl_[2];
 			const double2 *x_[2], *h_[2];
-			for (int e = 0; e < n_ent; e += 2) {
+			for (int e = 0; e < n_ent; e += Cfg::SLOTS) {
 #pragma unroll
 				for (int q = 0; q < 2; ++q) {
 					const int ee = e + q;
-					if (ee >= n_ent) { fl_[q] = 0; x_[q] = nullptr; h_[q] = nullptr; }
+					if (q >= Cfg::SLOTS || ee >= n_ent) { fl_[q] = 0; x_[q] = nullptr; h_[q] = nullptr; }
 					else if (ee == 0) {
 						const bool hh = a.pf < a.P;
 						fl_[q] = PC_BINIT | (hh ? PC_BHASH : 0); x_[q] = nullptr; h_[q] = hh ? Hc + (long) a.pf * N : nullptr;
@@ -571,11 +573,11 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 				if (n_ent == 0) { stage2(PC_SZERO | PC_SSTORE | last, nullptr, nullptr, 0, nullptr, nullptr, c, s); continue; }
 				int fl_[2];
 				const double2 *x_[2], *h_[2];
-				for (int e = 0; e < n_ent; e += 2) {
+				for (int e = 0; e < n_ent; e += Cfg::SLOTS) {
 #pragma unroll
 					for (int q = 0; q < 2; ++q) {
 						const int ee = e + q;
-						if (ee >= n_ent) { fl_[q] = 0; x_[q] = nullptr; h_[q] = nullptr; continue; }
+						if (q >= Cfg::SLOTS || ee >= n_ent) { fl_[q] = 0; x_[q] = nullptr; h_[q] = nullptr; continue; }
 						const int fin = (ee == n_ent - 1) ? (PC_SSTORE | last) : 0;
 						if (ee < a.pf - 1) {
 							const int p = ee + 1;

@@ -6,6 +6,7 @@ Q="--no-cpu --no-e2e --no-configs"
 summ() { python -c "import json,sys; d=json.load(open('$1')); print('$2', round(d['value']), round(d['ms_per_step']*1e3,1), round(d['roofline']['frac'],3), {k:(round(v['alone_us'],1), round(v.get('alone_frac',0),3)) for k,v in d['roofline'].get('kernels',{}).items()})" 2>&1 | tail -1; }
 timeout 900 python -m pytest tests/test_gpu_headline.py -m gpu -q --no-header -p no:cacheprovider -x > $O/pytest_headline.log 2>&1
 echo "pytest headline exit $?" >> $O/pytest_headline.log; tail -12 $O/pytest_headline.log
+for i in 1 2 3; do timeout 300 python -m pytest "tests/test_gpu_headline.py::test_pipe_more_channels_than_sms" -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -3; done
 timeout 300 python bench.py $Q > $O/c_mega.json 2> $O/c_mega.err; summ $O/c_mega.json mega; tail -3 $O/c_mega.err
 timeout 300 python scripts/pipe_stats.py > $O/pipe_stats.txt 2>&1; cat $O/pipe_stats.txt
 DSP_B200_FIR_PIPE_NOITEMS=1 timeout 300 python bench.py $Q > $O/c_noitems.json 2> $O/c_noitems.err; summ $O/c_noitems.json noitems
