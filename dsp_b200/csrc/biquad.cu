@@ -49,22 +49,38 @@ __device__ __forceinline__ double2 m2_apply(const M2 &m, double2 v)
 
 // CH adjacent channels share a CTA; a warp's lanes are (32 / CH consecutive chunks) x (CH channels), channel
 // fastest, so that one load instruction touches 32 / CH rows and uses CH x 8 contiguous bytes of each.
-template <int CH>
+// SPLIT: two CTAs per channel pair, each on one half (2048 frames) of a 4096-frame tile, 8 warps each -- two of
+// them fit an SM, so that one CTA's barriers, table loads and block I/O hide behind the other's arithmetic.  The
+// second half needs, per stage, the state the first half ends in: the first half publishes it (state, fence, flag)
+// as soon as its stage is done and the second half picks it up right before that stage's carry step, i.e. it runs
+// one stage behind (decoupled look-back along time; CTAs of the first half have the lower block indices, so they
+// are always scheduled before the CTAs that wait for them).
+template <int CH, bool SPLIT = false>
 struct BqCfg {
 	static_assert(CH == 1 || CH == 2 || CH == 4, "1, 2 or 4 channels per CTA");
+	static_assert(!SPLIT || CH == 2, "the split form is built for channel pairs");
 	static constexpr int CPW = 32 / CH;                         // chunks per warp
 	static constexpr int LOGW = (CH == 1) ? 5 : (CH == 2) ? 4 : 3;
-	static constexpr int WARPS = (CH == 1) ? 8 : 16;
+	static constexpr int WARPS = SPLIT ? 8 : (CH == 1) ? 8 : 16;
 	static constexpr int THREADS = 32 * WARPS;
 	static constexpr long TILE = (long) BQ_L * CPW * WARPS;     // frames per tile
 };
 
+struct BqSplitArgs {
+	double *xstate;   // [C][S][2]: state at the end of the first half, per stage
+	int *flag;        // [C][S]: == epoch once xstate[c][st] is valid
+	int epoch;
+};
+
 // tbl: [C][S][BQ_TBL] (see BQ_TBL), zstate: [C][S][2]
-template <int CH>
-__global__ void __launch_bounds__(BqCfg<CH>::THREADS) k_bq_cascade(const double *in, double *out, const double *__restrict__ tbl,
-                                                                  double *zstate, int C, int S, long frames)
+template <int CH, bool SPLIT = false>
+__global__ void __launch_bounds__(BqCfg<CH, SPLIT>::THREADS, SPLIT ? 2 : 1) k_bq_cascade(const double *in, double *out, const double *__restrict__ tbl,
+                                                                  double *zstate, int C, int S, long frames, BqSplitArgs sp)
 {
-	using Cfg = BqCfg<CH>;
+	using Cfg = BqCfg<CH, SPLIT>;
+	const int half = SPLIT ? (int) blockIdx.y : 0;
+	if (SPLIT && half == 1 && frames <= Cfg::TILE) return;   // nothing in the second half (the whole CTA leaves before any barrier)
+	const bool second_exists = SPLIT && frames > Cfg::TILE;
 	constexpr int LOGW = Cfg::LOGW;
 	__shared__ double2 tot[Cfg::WARPS][CH];
 	__shared__ double2 carry[BQ_MAX_STAGES][CH];
@@ -78,13 +94,14 @@ __global__ void __launch_bounds__(BqCfg<CH>::THREADS) k_bq_cascade(const double 
 	for (int i = threadIdx.x; i < nch * S * BQ_TBL; i += blockDim.x) stbl[i] = tbl[(long) c0 * S * BQ_TBL + i];
 	if (threadIdx.x < S * CH) {
 		const int st = threadIdx.x / CH, k = threadIdx.x % CH;
-		carry[st][k] = (k < nch) ? make_double2(zstate[((long) (c0 + k) * S + st) * 2], zstate[((long) (c0 + k) * S + st) * 2 + 1])
-		                         : make_double2(0.0, 0.0);
+		// (the second half's entries are filled stage by stage from the first half's published states)
+		carry[st][k] = (k < nch && half == 0) ? make_double2(zstate[((long) (c0 + k) * S + st) * 2], zstate[((long) (c0 + k) * S + st) * 2 + 1])
+		                                      : make_double2(0.0, 0.0);
 	}
 	__syncthreads();
 	const double *mytbl = stbl + (have ? ch : 0) * S * BQ_TBL;
 
-	for (long base = 0; base < frames; base += Cfg::TILE) {
+	for (long base = SPLIT ? half * Cfg::TILE : 0; base < frames; base += SPLIT ? frames : Cfg::TILE) {
 		const long f0 = base + ((long) w * Cfg::CPW + jl) * BQ_L;
 		const long rem = frames - f0;
 		const int nv = (rem <= 0 || !have) ? 0 : (rem < BQ_L ? (int) rem : BQ_L);
@@ -131,6 +148,14 @@ __global__ void __launch_bounds__(BqCfg<CH>::THREADS) k_bq_cascade(const double 
 			double2 z = make_double2(__shfl_up_sync(0xffffffffu, sc.x, CH), __shfl_up_sync(0xffffffffu, sc.y, CH));
 			if (jl == 0) z = make_double2(0.0, 0.0);
 			if (jl == Cfg::CPW - 1) tot[w][ch] = sc;
+			if (SPLIT && half == 1 && w == 0 && jl == 0 && have) {
+				// the state the first half left this stage in: wait for its flag, then read it past L1
+				const long o = (long) c * S + st;
+				volatile int *fl = sp.flag + o;
+				while (*fl != sp.epoch) { }
+				__threadfence();
+				carry[st][ch] = make_double2(__ldcg(&sp.xstate[o * 2]), __ldcg(&sp.xstate[o * 2 + 1]));
+			}
 			__syncthreads();
 			// (3) carry into this warp, then into this lane
 			double2 cin = carry[st][ch];
@@ -154,14 +179,23 @@ __global__ void __launch_bounds__(BqCfg<CH>::THREADS) k_bq_cascade(const double 
 				}
 			}
 			__syncthreads();   // everyone has read tot[] and carry[st]
-			if (last_chunk) carry[st][ch] = make_double2(m0, m1);
+			if (last_chunk) {
+				carry[st][ch] = make_double2(m0, m1);
+				if (SPLIT && half == 0 && second_exists) {
+					const long o = (long) c * S + st;
+					sp.xstate[o * 2] = m0;
+					sp.xstate[o * 2 + 1] = m1;
+					__threadfence();
+					*reinterpret_cast<volatile int *>(sp.flag + o) = sp.epoch;
+				}
+			}
 		}
 #pragma unroll
 		for (int i = 0; i < BQ_L; ++i)
 			if (i < nv) out[(f0 + i) * C + c] = y[i];
 		__syncthreads();   // carry[] complete before the next tile reads it
 	}
-	if (threadIdx.x < S * CH) {
+	if (threadIdx.x < S * CH && (!SPLIT || half == 1 || !second_exists)) {   // the CTA that holds the end of the block
 		const int st = threadIdx.x / CH, k = threadIdx.x % CH;
 		if (k < nch) {
 			zstate[((long) (c0 + k) * S + st) * 2] = carry[st][k].x;
@@ -173,7 +207,21 @@ __global__ void __launch_bounds__(BqCfg<CH>::THREADS) k_bq_cascade(const double 
 template <int CH>
 static int bq_launch(const double *in, double *out, const double *tbl, double *zstate, int C, int S, long frames, cudaStream_t st)
 {
-	LAUNCH((k_bq_cascade<CH>), (C + CH - 1) / CH, BqCfg<CH>::THREADS, (size_t) CH * S * BQ_TBL * sizeof(double), st, in, out, tbl, zstate, C, S, frames);
+	LAUNCH((k_bq_cascade<CH>), (C + CH - 1) / CH, BqCfg<CH>::THREADS, (size_t) CH * S * BQ_TBL * sizeof(double), st, in, out, tbl, zstate, C, S, frames, BqSplitArgs{});
+	return 0;
+}
+
+// split form: one launch per 4096 frames, two CTAs per channel pair
+static int bq_launch_split(const double *in, double *out, const double *tbl, double *zstate, int C, int S, long frames, cudaStream_t st, BqSplitArgs sp, int *epoch)
+{
+	using Cfg = BqCfg<2, true>;
+	const long span = 2 * Cfg::TILE;
+	for (long base = 0; base < frames; base += span) {
+		const long n = (frames - base < span) ? frames - base : span;
+		sp.epoch = ++*epoch;
+		LAUNCH((k_bq_cascade<2, true>), dim3((C + 1) / 2, 2), Cfg::THREADS, (size_t) 2 * S * BQ_TBL * sizeof(double), st, in + base * C, out + base * C, tbl,
+		       zstate, C, S, n, sp);
+	}
 	return 0;
 }
 
@@ -181,6 +229,9 @@ struct BiquadOp : Op {
 	int S = 0;
 	std::vector<double> h_coefs;   // [S][C][5] as handed in (kept so neighbouring cascades can be fused)
 	double *d_tbl = nullptr, *d_zstate = nullptr;
+	double *d_xstate = nullptr;   // split form: per-stage state between the two halves of a tile
+	int *d_flag = nullptr;
+	int epoch = 0;
 
 	const char *name() const override { return "biquad"; }
 	std::string describe() const override
@@ -189,7 +240,7 @@ struct BiquadOp : Op {
 		snprintf(buf, sizeof(buf), "{\"op\":\"biquad\",\"stages\":%d}", S);
 		return buf;
 	}
-	~BiquadOp() override { dev_free(d_tbl); dev_free(d_zstate); }
+	~BiquadOp() override { dev_free(d_tbl); dev_free(d_zstate); dev_free(d_xstate); dev_free(d_flag); }
 
 	void reset(cudaStream_t st) override
 	{
@@ -205,8 +256,13 @@ struct BiquadOp : Op {
 		// Always channel pairs: the scan's association order depends on the chunks per warp, and a channel's
 		// result must not depend on how the chain was sharded (tests: sharded == unsharded, bit for bit).
 		const int chp = force ? force : 2;
+		static const int split = getenv("DSP_B200_BQ_SPLIT") ? atoi(getenv("DSP_B200_BQ_SPLIT")) : 1;
 		int rc;
-		if (chp == 4) rc = bq_launch<4>(in, out, d_tbl, d_zstate, channels, S, frames, st);
+		if (chp == 2 && split) {
+			BqSplitArgs sp = { d_xstate, d_flag, 0 };
+			rc = bq_launch_split(in, out, d_tbl, d_zstate, channels, S, frames, st, sp, &epoch);
+		}
+		else if (chp == 4) rc = bq_launch<4>(in, out, d_tbl, d_zstate, channels, S, frames, st);
 		else if (chp == 2) rc = bq_launch<2>(in, out, d_tbl, d_zstate, channels, S, frames, st);
 		else rc = bq_launch<1>(in, out, d_tbl, d_zstate, channels, S, frames, st);
 		return rc ? -1 : frames;
@@ -257,7 +313,9 @@ Op *make_biquad_op(int slab_channels, int fs, int n_stages, const double *coefs)
 	}
 	op->d_tbl = dev_alloc<double>(tbl.size(), false);
 	op->d_zstate = dev_alloc<double>((size_t) C * S * 2, true);
-	if (!op->d_tbl || !op->d_zstate) return nullptr;
+	op->d_xstate = dev_alloc<double>((size_t) C * S * 2, true);
+	op->d_flag = dev_alloc<int>((size_t) C * S, true);
+	if (!op->d_tbl || !op->d_zstate || !op->d_xstate || !op->d_flag) return nullptr;
 	CUDA_TRY(cudaMemcpy(op->d_tbl, tbl.data(), tbl.size() * sizeof(double), cudaMemcpyHostToDevice), return nullptr);
 	return op.release();
 }

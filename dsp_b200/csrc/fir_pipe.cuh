@@ -15,7 +15,7 @@
 //                                 mbarrier) and tags every stage with a command word.  It issues the stages of (a) as
 //                                 soon as the spectrum buffer `sbuf` is free for the channel and fills all other time
 //                                 with its share of the work items of (b) -- the HBM stream never waits for a transform.
-//   MAC warps (8)                 execute the command of each stage: complex multiply-accumulate of 512 bins (2 per
+//   MAC warps (4)                 execute the command of each stage: complex multiply-accumulate of 256 bins (2 per
 //                                 lane) into registers, sums of (a) dropped into `sbuf`, sums of (b) stored to V
 //   transform team (N/16 threads) reads the caller's interleaved block, forward FFT in shared memory, spectrum to the
 //                                 FDL, S = sbuf + X_j H_0 for the bin pairs it owns, inverse FFT in place,
@@ -36,13 +36,13 @@ constexpr int PIPE_TB = 4;   // batch depth of (b): outputs per pass, = number o
 template <int N>
 struct PipeCfg {
 	static constexpr int TF = N / 16;                 // transform team (one FFT)
-	static constexpr int MAC_WARPS = 8;               // one bin per lane and row pair: 2 MAC warps per scheduler hide each other's latencies
+	static constexpr int MAC_WARPS = 4;               // 8 + 4 + 1 warps: at most 4 warps per SM sub-partition, 128 registers each
 	static constexpr int TM = MAC_WARPS * 32;
-	static constexpr int THREADS = TF + TM + 128;     // + the producer's warpgroup (register reallocation works on groups of 4 warps)
-	static constexpr int CHUNK = 512;                 // bins per row chunk: 8 KB per bulk copy (a copy costs the issuing thread ~220 cycles whatever its size)
+	static constexpr int THREADS = TF + TM + 32;      // + producer warp
+	static constexpr int CHUNK = 256;                 // bins per stage
 	static constexpr int NCHUNK = N / CHUNK;
 	static constexpr int PER = CHUNK / TM;            // bins per MAC lane and stage
-	static constexpr int SLOTS = 1;                   // (X chunk | H chunk) pairs per stage
+	static constexpr int SLOTS = 2;                   // (X chunk | H chunk) pairs per stage: one barrier round trip per two rows
 	static constexpr int NS = (N >= 4096) ? 5 : 8;    // ring stages (16 KB each)
 	static constexpr size_t STAGE_BYTES = SLOTS * 2 * (size_t) CHUNK * sizeof(double2);
 	static constexpr size_t FBUF = (size_t) FftCfg<N>::STRIDE * sizeof(double2);
@@ -185,9 +185,8 @@ __device__ __forceinline__ void pipe_prefetch_rows(const void *p, long bytes, in
 // round-robin: 13 warps = at most 4 per sub-partition = 128 registers per thread (a 17-warp layout with 8 MAC warps
 // would have to fit 5 x 32 x R <= 16384, i.e. 96 registers, which the transform team cannot live with).
 #ifndef FIR_PIPE_MAXNREG
-#define FIR_PIPE_MAXNREG 96
+#define FIR_PIPE_MAXNREG 128
 #endif
-#define FIR_PIPE_SETMAXNREG 1
 
 template <int N>
 __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
@@ -222,7 +221,6 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		// ------------------------------------------------------------------------------------------
 		// transform team
 		// ------------------------------------------------------------------------------------------
-		asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
 		const int t = threadIdx.x;
 		double2 *buf = fbuf;
 		int it = 0;
@@ -337,7 +335,6 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		// ------------------------------------------------------------------------------------------
 		// MAC warps: execute the stages' commands
 		// ------------------------------------------------------------------------------------------
-		asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
 		const int tm = threadIdx.x - T;
 		int stage = 0;
 		unsigned phase = 0;
@@ -460,11 +457,9 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			a.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
 		}
 	}
-	else {
-	asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-	if (warp == T / 32 + Cfg::MAC_WARPS && elect_one()) {
+	else if (elect_one()) {
 		// ------------------------------------------------------------------------------------------
-		// producer / scheduler (one elected lane of the first warp of the last warpgroup)
+		// producer / scheduler (one elected lane of the last warp)
 		// ------------------------------------------------------------------------------------------
 		const uint64_t pol = l2_policy_evict_first();
 		const bool hint_x = a.evict_first != 0, hint_h = a.evict_first != 0 && a.h_ch_stride != 0;
@@ -477,29 +472,38 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 		unsigned phase = 0;
 		long n_stages = 0;
 
-		// One stage = up to two (X chunk | H chunk) row pairs of one chunk of one channel: wait for the ring slot, tag
-		// it, start the copies.  (This thread runs alone: every instruction costs its full latency, so the path is
-		// kept short -- no pending state, pointers advanced by the callers.)
-		static_assert(Cfg::SLOTS == 1 || Cfg::SLOTS == 2, "stage2() fills one or two row pairs");
-		auto stage2 = [&](int fl0, const double2 *x0, const double2 *h0, int fl1, const double2 *x1, const double2 *h1, int chunk, int s) {
+		// Stages carry up to SLOTS (X chunk | H chunk) pairs of one chunk of one channel: entries are collected with
+		// emit() and leave with flush() -- wait for the ring slot, tag it, start the copies.
+		static_assert(Cfg::SLOTS == 2, "the pending stage is kept in scalars");
+		int pn = 0, p_chunk = 0, p_s = 0, p_fl0 = 0, p_fl1 = 0;
+		const double2 *p_x0 = nullptr, *p_h0 = nullptr, *p_x1 = nullptr, *p_h1 = nullptr;
+		bool p_hx0 = false, p_hh0 = false, p_hx1 = false, p_hh1 = false;
+		auto flush = [&]() {
+			if (pn == 0) return;
 			{
 				const long long t0 = stats_on ? clock64() : 0;
 				mbar_wait(&empty[stage], phase ^ 1);
 				if (stats_on) t_wait += clock64() - t0;
 			}
-			const unsigned bytes = (x0 ? ROW_BYTES : 0) + (h0 ? ROW_BYTES : 0) + (x1 ? ROW_BYTES : 0) + (h1 ? ROW_BYTES : 0);
-			cmds[stage] = make_int4(fl0 | (fl1 << 16), chunk, s, 0);
+			if (pn < 2) { p_fl1 = 0; p_x1 = nullptr; p_h1 = nullptr; }
+			const unsigned bytes = (p_x0 ? ROW_BYTES : 0) + (p_h0 ? ROW_BYTES : 0) + (p_x1 ? ROW_BYTES : 0) + (p_h1 ? ROW_BYTES : 0);
+			cmds[stage] = make_int4(p_fl0 | (p_fl1 << 16), p_chunk, p_s, 0);
 			if (bytes) mbar_arrive_expect_tx(&full[stage], bytes);
 			else mbar_arrive(&full[stage]);   // nothing to copy (exit, or rows that do not exist)
 			double2 *dst = ring + (size_t) stage * Cfg::SLOTS * 2 * CHUNK;
-			if (x0) bulk_g2s(dst, x0, ROW_BYTES, &full[stage], hint_x, pol);
-			if (h0) bulk_g2s(dst + CHUNK, h0, ROW_BYTES, &full[stage], hint_h, pol);
-			if (Cfg::SLOTS > 1) {
-				if (x1) bulk_g2s(dst + 2 * CHUNK, x1, ROW_BYTES, &full[stage], hint_x, pol);
-				if (h1) bulk_g2s(dst + 3 * CHUNK, h1, ROW_BYTES, &full[stage], hint_h, pol);
-			}
+			if (p_x0) bulk_g2s(dst, p_x0, ROW_BYTES, &full[stage], p_hx0, pol);
+			if (p_h0) bulk_g2s(dst + CHUNK, p_h0, ROW_BYTES, &full[stage], p_hh0, pol);
+			if (p_x1) bulk_g2s(dst + 2 * CHUNK, p_x1, ROW_BYTES, &full[stage], p_hx1, pol);
+			if (p_h1) bulk_g2s(dst + 3 * CHUNK, p_h1, ROW_BYTES, &full[stage], p_hh1, pol);
 			if (++stage == NS) { stage = 0; phase ^= 1; }
 			++n_stages;
+			pn = 0;
+		};
+		auto emit = [&](int flags, int chunk, int s, const double2 *xsrc, const double2 *hsrc, bool hx, bool hh) {
+			if (pn == 0) { p_fl0 = flags; p_x0 = xsrc; p_h0 = hsrc; p_hx0 = hx; p_hh0 = hh; }
+			else { p_fl1 = flags; p_x1 = xsrc; p_h1 = hsrc; p_hx1 = hx; p_hh1 = hh; }
+			p_chunk = chunk; p_s = s;
+			if (++pn == 2) flush();
 		};
 
 		// (b): the channels s = g + TB k of this block's residue g, cut into NCHUNK items each; this CTA's share
@@ -530,71 +534,38 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			const int s = g + TB * k;
 			const double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride + c * CHUNK;
 			const double2 *Hc = a.H + (long) s * a.h_ch_stride + c * CHUNK;
-			// entry 0 loads the window: window[t] = H_{3+t} where it belongs to the batch (p >= pf): with pf = TB + 2 only
-			// t = TB-1 does.  Entry e >= 1 is step m = e + 2: X_{j+2-m} (one row further back per step, starting at
-			// block j-1) meets the window; next window row H_{m+TB}.
-			const int n_ent = a.P - 2;
+			// window[t] = H_{3+t} where it belongs to the batch (p >= pf): with pf = TB + 2 only t = TB-1 does
+			const int p0 = a.pf;
+			emit(PC_BINIT | ((p0 < a.P) ? PC_BHASH : 0), c, s, nullptr, (p0 < a.P) ? Hc + (long) p0 * N : nullptr, false, hint_h);
+			// step m: X_{j+2-m} (one row further back per step, starting at block j-1) meets the window; next window row H_{m+TB}
 			int sl = a.slot - 1;
 			if (sl < 0) sl += a.fdl_rows;
-			const double2 *hp = Hc + (long) (3 + TB) * N;   // H_{m+TB} for m = 3
-			int fl_[2];
-			const double2 *x_[2], *h_[2];
-			for (int e = 0; e < n_ent; e += Cfg::SLOTS) {
-#pragma unroll
-				for (int q = 0; q < 2; ++q) {
-					const int ee = e + q;
-					if (q >= Cfg::SLOTS || ee >= n_ent) { fl_[q] = 0; x_[q] = nullptr; h_[q] = nullptr; }
-					else if (ee == 0) {
-						const bool hh = a.pf < a.P;
-						fl_[q] = PC_BINIT | (hh ? PC_BHASH : 0); x_[q] = nullptr; h_[q] = hh ? Hc + (long) a.pf * N : nullptr;
-					}
-					else {
-						const int m = ee + 2;
-						const bool hh = m + TB < a.P;
-						fl_[q] = PC_BSTEP | (hh ? PC_BHASH : 0) | ((m == a.P - 1) ? PC_BSTORE : 0);
-						x_[q] = fdl + (long) sl * N;
-						h_[q] = hh ? hp : nullptr;
-						hp += N;
-						if (--sl < 0) sl += a.fdl_rows;
-					}
-				}
-				stage2(fl_[0], x_[0], h_[0], fl_[1], x_[1], h_[1], c, s);
+			const double2 *hp = Hc + (long) (3 + TB) * N;
+			for (int m = 3; m < a.P; ++m) {
+				const bool hh = m + TB < a.P;
+				emit(PC_BSTEP | (hh ? PC_BHASH : 0) | ((m == a.P - 1) ? PC_BSTORE : 0), c, s, fdl + (long) sl * N, hh ? hp : nullptr, hint_x, hint_h);
+				hp += N;
+				if (--sl < 0) sl += a.fdl_rows;
 			}
+			flush();
 		};
 
 		auto emit_channel = [&](int s) {
 			const double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride;
 			const double2 *Hc = a.H + (long) s * a.h_ch_stride;
 			const double2 *Vc = has_v ? a.V + ((a.blk % a.v_slots) * a.n_ch + s) * (long) N : nullptr;
-			// entries of a chunk: partitions 1 .. pf-1, then V_j; the last entry stores the sum
-			const int n_ent = a.pf - 1 + (Vc ? 1 : 0);
 			for (int c = 0; c < NCHUNK; ++c) {
 				const int last = (c == NCHUNK - 1) ? PC_SFULL : 0;
-				if (n_ent == 0) { stage2(PC_SZERO | PC_SSTORE | last, nullptr, nullptr, 0, nullptr, nullptr, c, s); continue; }
-				int fl_[2];
-				const double2 *x_[2], *h_[2];
-				for (int e = 0; e < n_ent; e += Cfg::SLOTS) {
-#pragma unroll
-					for (int q = 0; q < 2; ++q) {
-						const int ee = e + q;
-						if (q >= Cfg::SLOTS || ee >= n_ent) { fl_[q] = 0; x_[q] = nullptr; h_[q] = nullptr; continue; }
-						const int fin = (ee == n_ent - 1) ? (PC_SSTORE | last) : 0;
-						if (ee < a.pf - 1) {
-							const int p = ee + 1;
-							int sl = a.slot - p;
-							if (sl < 0) sl += a.fdl_rows;
-							fl_[q] = PC_SMAC | (p == 1 ? PC_SZERO : 0) | fin;
-							x_[q] = fdl + (long) sl * N + c * CHUNK;
-							h_[q] = Hc + (long) p * N + c * CHUNK;
-						}
-						else {
-							fl_[q] = PC_SADDV | fin | (a.pf <= 1 ? PC_SZERO : 0);
-							x_[q] = Vc + c * CHUNK;
-							h_[q] = nullptr;
-						}
-					}
-					stage2(fl_[0], x_[0], h_[0], fl_[1], x_[1], h_[1], c, s);
+				if (a.pf <= 1 && !Vc) { emit(PC_SZERO | PC_SSTORE | last, c, s, nullptr, nullptr, false, false); flush(); continue; }
+				for (int p = 1; p < a.pf; ++p) {
+					int sl = a.slot - p;
+					if (sl < 0) sl += a.fdl_rows;
+					int fl = PC_SMAC | (p == 1 ? PC_SZERO : 0);
+					if (p == a.pf - 1 && !Vc) fl |= PC_SSTORE | last;
+					emit(fl, c, s, fdl + (long) sl * N + c * CHUNK, Hc + (long) p * N + c * CHUNK, hint_x, hint_h);
 				}
+				if (Vc) emit(PC_SADDV | PC_SSTORE | last | (a.pf <= 1 ? PC_SZERO : 0), c, s, Vc + c * CHUNK, nullptr, hint_x, false);
+				flush();   // a stage never mixes chunks
 			}
 		};
 
@@ -612,14 +583,14 @@ __global__ void __maxnreg__(FIR_PIPE_MAXNREG) k_fir_pipe(PipeArgs a)
 			}
 			else break;
 		}
-		stage2(PC_EXIT, nullptr, nullptr, 0, nullptr, nullptr, 0, 0);
+		emit(PC_EXIT, 0, 0, nullptr, nullptr, false, false);
+		flush();
 		if (stats_on) {
 			a.stats[blockIdx.x * 8 + 2] = t_wait;
 			a.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;
 			a.stats[blockIdx.x * 8 + 6] = n_stages;
 			a.stats[blockIdx.x * 8 + 7] = item_end - item0;
 		}
-	}
 	}
 }
 

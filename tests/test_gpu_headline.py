@@ -1,8 +1,9 @@
-"""GPU tier: the exact kernel composition of the BASELINE headline (single level of 4096-frame partitions, the
-persistent pipeline kernel k_fir_pipe + the time-batched tail k_fir_mac_batch) against the COMPILED reference
-(oracle/_ref, fir_p.c unmodified) on random data long enough for every partition to meet non-zero blocks, plus the
-variants of that composition: the pre-pipeline kernels (DSP_B200_FIR_PIPE=0) at batch depth 4/6/8, more channels than
-SMs (a CTA walks two channels), shared filter, selectors, 2048-frame partitions, BASELINE config 3 (64 channels)."""
+"""GPU tier: the exact kernel composition of the BASELINE headline (single level of 4096-frame partitions: fused
+block kernel k_fir_level0 in its cluster form + per-block k_fir_mac + time-batched k_fir_mac_batch on three streams)
+against the COMPILED reference (oracle/_ref, fir_p.c unmodified) on random data long enough for every partition to meet
+non-zero blocks, at batch depth 4/6/8 -- and the same for the opt-in one-kernel-per-block pipeline (k_fir_pipe,
+DSP_B200_FIR_PIPE=1): more channels than SMs (a CTA walks two or three channels), shared filter, selectors, ragged
+calls mixed in, 2048-frame partitions; BASELINE config 3 (64 channels) at full size."""
 import os
 from contextlib import contextmanager
 
@@ -72,8 +73,9 @@ def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_
     assert np.max(np.abs(got - want)) <= 1e-9
 
 
+@pytest.mark.parametrize("pipe", [1, 0])
 @pytest.mark.parametrize("taps,shared", [(30000, True), (50000, True), (50000, False), (9000, False)])
-def test_pipe_more_channels_than_sms(gpu_lib, taps, shared):
+def test_pipe_more_channels_than_sms(gpu_lib, taps, shared, pipe):
     """300 channels: the persistent grid has one CTA per SM, so most CTAs walk two channels (ring, sbuf hand-over and
     barrier phases cross a channel boundary).  30000 taps = 8 partitions (all summed in the kernel, no batch), 50000 =
     13 (batched tail), 9000 = 3.  8 distinct signals tiled over the channels; the first 8 channels against the
@@ -88,9 +90,10 @@ def test_pipe_more_channels_than_sms(gpu_lib, taps, shared):
         h = restate.bench_ir(taps)
     else:
         h = np.stack([restate.bench_ir(taps, c % 5) for c in range(C)], axis=1)
-    ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
-    plan = ch.describe()[0]
-    assert plan["pipe"] == 1 and len(plan["levels"]) == 1, plan
+    with env(DSP_B200_FIR_PIPE=pipe):
+        ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
+        plan = ch.describe()[0]
+    assert plan["pipe"] == pipe and len(plan["levels"]) == 1, plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, nblk * F, F)])
     ch.close()
     if shared:
@@ -105,7 +108,8 @@ def test_pipe_more_channels_than_sms(gpu_lib, taps, shared):
         assert np.array_equal(got[:, 0], got[:, 40]) and np.array_equal(got[:, 3], got[:, 203])
 
 
-def test_pipe_selector_latency_and_ragged_mix(gpu_lib):
+@pytest.mark.parametrize("pipe", [1, 0])
+def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe):
     """The pipeline kernel behind a scattered selector, writing into the compact buffer of fir's latency ring, with
     whole blocks and ragged calls alternating on the same state (general path <-> pipeline kernel, batched V kept
     current by both)."""
@@ -118,9 +122,10 @@ def test_pipe_selector_latency_and_ragged_mix(gpu_lib):
         N = 22 * F + 333
         x = rng.standard_normal((N, C)) * 0.2
         want = restate.fir_stream(x, h, selector=sel, latency=lat)
-        ch = gpu_lib.Chain(fs, C).add_fir(h, selector=sel, latency=lat, block_hint=F)
-        plan = ch.describe()[0]
-        assert plan["pipe"] == 1 and plan["t_batch"] == 4, plan
+        with env(DSP_B200_FIR_PIPE=pipe):
+            ch = gpu_lib.Chain(fs, C).add_fir(h, selector=sel, latency=lat, block_hint=F)
+            plan = ch.describe()[0]
+        assert plan["pipe"] == pipe and plan["t_batch"] == 4, plan
         cuts = [0, F, 2 * F, 2 * F + 100, 3 * F, 4 * F, 5 * F, 6 * F, 7 * F, 7 * F + 1, 8 * F - 1, 8 * F, 9 * F, 10 * F, 11 * F, 12 * F,
                 12 * F + 2000, 14 * F, 15 * F, 16 * F, 17 * F, 18 * F, 19 * F, 20 * F, 21 * F, 22 * F, N]
         got = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
@@ -146,7 +151,7 @@ def test_pipe_2048_frame_partitions(gpu_lib, taps):
     N = 40 * F
     x = rng.standard_normal((N, C)) * 0.2
     want = restate.fir_stream(x, h)
-    with env(DSP_B200_FIR_LEVEL_CAP="2048"):
+    with env(DSP_B200_FIR_LEVEL_CAP="2048", DSP_B200_FIR_PIPE=1):
         ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
         plan = ch.describe()[0]
     assert plan["pipe"] == 1 and plan["levels"][0]["B"] == 2048 and len(plan["levels"]) == 1, plan
