@@ -410,6 +410,28 @@ def measure_configs(dsp, torch, irs, peak, local_rank, dropin_steps):
             dd["api"] = "run_effects_chain() (reference effects_chain.c, unmodified) -> shim effect->run() -> dspb200_chain_run_host, in place; clock_gettime around each call"
             dd["workload"] = "fir_p 131072 taps x 256 ch, 4096-frame blocks (the headline through the drop-in)"
             out["e2e_dropin"] = dd
+            # config 5's chain through the drop-in: eight eq + fir_p 65536 (shared IR) + resample -- the optimizer merges the
+            # same-rate effects, the device hand-off carries the block across the rate change: one device chain per block
+            tmp = tempfile.mkdtemp(prefix="dspb200_dropin_")
+            ir_path = os.path.join(tmp, "ir5.f64")
+            make_ir(65536, 0).astype("<f8").tofile(ir_path)
+            eqs = " ".join("eq %g 1.4 %g" % (EQ_F[i], EQ_G[i]) for i in range(8))
+            chain5 = "%s fir_p -t pcm -e double -c 1 -r 44100 %s resample 48k" % (eqs, ir_path)
+            os.environ["DSP_B200_PIN"] = "1"
+            fc = frontend.DropinChain(chain5, 44100, C)
+            h0, d0 = dsp.copy_counts()
+            sec, f, chk = fc.time(pool, 5, dropin_steps)
+            h1, d1 = dsp.copy_counts()
+            out["C5_dropin"] = {"workload": "8 x eq + fir_p 65536 (shared IR) + resample 44100 -> 48000, 256 ch, 4096-frame blocks, run_effects_chain() through the drop-in",
+                                "value": C * F * dropin_steps / sec / 1e6, "unit": UNIT, "ms_per_block": sec / dropin_steps * 1e3, "blocks": dropin_steps,
+                                "effects": fc.effect_names(), "h2d_copies_per_block": (h1 - h0) / float(dropin_steps + 5),
+                                "d2h_copies_per_block": (d1 - d0) / float(dropin_steps + 5),
+                                "note": "copies are counted per channel slab (4 slabs at 256 channels): one copy in and one out per slab and block = one device chain across the rate change",
+                                "checksum": chk}
+            fc.close()
+            os.environ.pop("DSP_B200_PIN", None)
+            os.remove(ir_path)
+            os.rmdir(tmp)
         else:
             out["e2e_dropin"] = {"unavailable": "shim/_build/libdsp_b200_frontend.so not built (needs the reference sources at build time)"}
     except Exception as ex:                                            # a failing side measurement must not sink the headline
@@ -475,6 +497,7 @@ def main():
         emit(line)
         return 0
 
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream of every chain this process builds (before CUDA starts)
     import torch
     import dsp_b200
     from dsp_b200.dist import Job

@@ -293,6 +293,15 @@ struct dspb200_chain {
 	}
 };
 
+// The operators run work on several streams at once (K2: block kernel, look-ahead MAC, batched MAC).  CUDA multiplexes
+// streams onto a small number of hardware queues (8 by default); in a process that has created and destroyed many
+// streams, two streams of one operator can land on the same queue and silently serialise.  Ask for more queues
+// before the CUDA context exists (no effect if the host application already decided, or initialised CUDA first).
+__attribute__((constructor)) static void dspb200_more_hw_queues()
+{
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+
 static bool g_probe_ok()
 {
 	int n = 0;

@@ -256,7 +256,13 @@ struct BiquadOp : Op {
 		// Always channel pairs: the scan's association order depends on the chunks per warp, and a channel's
 		// result must not depend on how the chain was sharded (tests: sharded == unsharded, bit for bit).
 		const int chp = force ? force : 2;
-		static const int split = getenv("DSP_B200_BQ_SPLIT") ? atoi(getenv("DSP_B200_BQ_SPLIT")) : 1;
+		// Split form (two 8-warp CTAs per channel pair with a per-stage look-back of the first half's state): measured
+		// SLOWER than one 16-warp CTA on full tiles (35.3 vs 26.7 us on config 2: the second half trails by a stage and
+		// the two CTAs of a pair contend for the same SM's FP64 pipe instead of hiding each other) -- but calls of at
+		// most 2048 frames have no second half, and 8 warps on such a block beat 16 half-idle ones (16.4 vs 20.6 us at 512
+		// frames).  DSP_B200_BQ_SPLIT=1 forces it everywhere, =0 nowhere.
+		static const int split_env = getenv("DSP_B200_BQ_SPLIT") ? atoi(getenv("DSP_B200_BQ_SPLIT")) : -1;
+		const bool split = (split_env >= 0) ? split_env != 0 : frames <= BqCfg<2, true>::TILE;
 		int rc;
 		if (chp == 2 && split) {
 			BqSplitArgs sp = { d_xstate, d_flag, 0 };
