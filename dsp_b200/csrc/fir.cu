@@ -1172,7 +1172,11 @@ struct FirOp : Op {
 			if ((l > 0 || has_tail) && !side) {
 				int lo = 0, hi = 0;
 				cudaDeviceGetStreamPriorityRange(&lo, &hi);
-				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo), return -1);
+				// multi-level plans: the side stream carries the upper levels' block kernels, whose result the caller's
+				// stream waits for at its next block -- they must not queue behind the batched MAC's CTAs (measured: the
+				// same 2048-frame-block run took 68 or 350 us per block depending on who got the SMs first).  Single-level
+				// plans only keep look-ahead MACs there: lowest priority.
+				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, (n_levels > 1) ? hi : lo), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_urgent, cudaEventDisableTiming), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_tail[0], cudaEventDisableTiming), return -1);

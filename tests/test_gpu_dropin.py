@@ -326,3 +326,26 @@ def test_device_chain_continues_across_align_and_resample(dropin, gpu_lib, have_
             assert counts == list(wcounts) and rms(got - want) <= RMS_TOL
     finally:
         os.environ.pop("DSP_B200_NO_LINK", None)
+
+
+def test_delay_between_gpu_effects_keeps_one_device_chain(dropin, gpu_lib, have_ref):
+    """`delay` hands its whole-sample part to the chain's align pass (delay.c:153-157,199) and is itself reorderable:
+    the GPU effects around it still merge into one device chain (one copy in, at most one out per call), the align
+    effect the chain appends realises the delays (on the device when it lands next to a GPU effect, else the
+    reference's own), and the stream equals the pure reference's."""
+    if not have_ref:
+        pytest.skip("compiled reference did not travel")
+    chain = "eq 1k 1.0 3 :0 delay 37S : eq 200 1.0 2 :1 delay 5S : lowshelf 300 0.7 -2"
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((4000, 2)) * 0.2
+    a = dropin.RefChain(chain, 48000, 2)
+    b = dropin.RefChain(chain, 48000, 2, lib_path=DROPIN)
+    assert "align" in b.effect_names()
+    ya, ca = a.process(x, 512)
+    h0, d0 = gpu_lib.copy_counts()
+    yb, cb = b.process(x, 512)
+    h1, d1 = gpu_lib.copy_counts()
+    assert ca == cb
+    assert rms(ya - yb) <= RMS_TOL, rms(ya - yb)
+    calls = len(cb)
+    assert h1 - h0 == calls and d1 - d0 <= calls, (h1 - h0, d1 - d0, calls)
