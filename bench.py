@@ -301,12 +301,20 @@ def fir_bytes_model(plan, C, F, h):
         mac = 16.0 * (P * (1 + h) + 1)
         batch = 0.0
     elif tb:
+        # per-block MAC: partitions pf .. pf+tb-1 (a row of X and of H each), V in, Y out.  A batch tier of depth T over
+        # n partitions streams n + T - 1 rows of X and n of H once for T block periods, writes T rows of V and -- the
+        # near tier of two -- reads the far tier's T rows
         mac = 16.0 * (tb * (1 + h) + 2)
-        batch = 16.0 * ((P - pf - 1) + (P - pf - tb) * h + tb) / tb
+        tf = int(plan.get("t_far", 0))
+        n_near = (tf + pf if tf else P) - (tb + pf)
+        batch = 16.0 * ((n_near + tb - 1) + n_near * h + tb + (tb if tf else 0)) / tb
+        far = 16.0 * ((P - pf - 1) + (P - pf - tf) * h + tf) / tf if tf else 0.0
     else:
         mac = 16.0 * ((P - pf) * (1 + h) + 1)
         batch = 0.0
     parts = {"stash_unstash": 0.0, "fir_level0": 0.0, "fir_fwd_inv": 0.0, "fir_mac": mac, "fir_mac_batch": batch}
+    if pf and tb and int(plan.get("t_far", 0)):
+        parts["fir_mac_batch_far"] = far
     direct = n_lv == 1 and (pf != 0 or P <= 2)
     if not direct:
         parts["stash_unstash"] = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)
@@ -543,13 +551,13 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "step:C%d:F%d:taps%d:h%d:pipe%d" % (C, F, a.taps, h, int(plan.get("pipe", 0)))
+        key = "step:C%d:F%d:taps%d:h%d:pipe%d:far%d" % (C, F, a.taps, h, int(plan.get("pipe", 0)), int(plan.get("t_far", 0)))
         traffic = tr.get(key, {}).get("dram_bytes_per_step")
     except Exception:
         pass
     step_s = ms / steps * 1e-3
     ach = per_sample * C * F / step_s / 1e9
-    knames = ("fir_pipe", "fir_level0", "fir_mac", "fir_mac_batch", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk")
+    knames = ("fir_pipe", "fir_level0", "fir_mac", "fir_mac_batch", "fir_mac_batch_far", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk")
     roofline = {"bound": "hbm",
                 "kernel": "one step = every kernel of the chain for one block, the look-ahead MACs on their own streams",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
@@ -586,7 +594,9 @@ def main():
             e = {"launches_per_step": n_l / float(n_iso), "alone_us": t_ms / n_l * 1e3}
             if per_launch:
                 # bytes_per_sample_by_kernel is per input sample; a launch of the batch kernel covers t_batch block periods
-                mult = plan.get("t_batch", 1) if nme == "fir_mac_batch" else 1
+                # (staggered: a launch covers 1/T of the channels for T periods = one block period's share)
+                depth = {"fir_mac_batch": plan.get("t_batch", 1), "fir_mac_batch_far": plan.get("t_far", 1)}.get(nme, 1)
+                mult = 1 if plan.get("stagger") else depth
                 e["algorithmic_bytes_per_launch"] = per_launch * nB * mult
                 e["alone_GBs"] = e["algorithmic_bytes_per_launch"] / (e["alone_us"] * 1e-6) / 1e9
                 e["alone_frac"] = e["alone_GBs"] / peak

@@ -308,8 +308,9 @@ __device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 h)
 	return make_double2(fma(x.x, h.x, fma(-x.y, h.y, acc.x)), fma(x.x, h.y, fma(x.y, h.x, acc.y)));
 }
 
-// CL: launched as clusters of 4 CTAs = 4 ADJACENT channels that do the direct-form I/O together: every CTA reads
-// a quarter of the rows for all four channels (32 contiguous bytes per row: whole sectors, 128-bit loads) and
+// CL: launched as clusters of 4 / CPB CTAs = 4 ADJACENT channels (four CTAs of one 4096- or 8192-point transform, two
+// CTAs of two 2048-point transforms) that do the direct-form I/O together: every CTA reads
+// its share of the rows for all four channels (32 contiguous bytes per row: whole sectors, 128-bit loads) and
 // drops each channel's samples into its owner's transform buffer through distributed shared memory; results
 // travel back the same way.  (One channel per CTA reads 8 of every 32-byte sector it touches: the fused kernel
 // took 43 us that way against 30 us with staged per-channel copies.)
@@ -321,7 +322,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 {
 	extern __shared__ double2 smem[];
 	constexpr int T = FftCfg<N>::T, CPB = FftCfg<N>::CPB;
-	static_assert(!CL || CPB == 1, "cluster I/O: one channel per CTA");
+	static_assert(!CL || CPB <= 2, "cluster I/O: four adjacent channels in 4 / CPB CTAs");
+	constexpr int NCL = CL ? 4 / CPB : 1;          // CTAs per cluster
+	constexpr int NPC = N / 2 / NCL;               // packed frame pairs a CTA moves for all four channels
+	constexpr int THREADS = FftCfg<N>::THREADS;
 	const int g = threadIdx.x / T, t = threadIdx.x % T;
 	const int s = blockIdx.x * CPB + g;
 	const bool active = s < a.n_ch;
@@ -333,18 +337,18 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		cg::cluster_group cluster = cg::this_cluster();
 		crank = cluster.block_rank();
 #pragma unroll
-		for (int c = 0; c < 4; ++c) rbuf[c] = cluster.map_shared_rank(buf, c);
+		for (int c = 0; c < 4; ++c) rbuf[c] = cluster.map_shared_rank(smem + (size_t) (c % CPB) * FftCfg<N>::STRIDE, c / CPB);
 		cluster.sync();   // a CTA's shared memory may only be touched once that CTA is known to be running
 	}
 
 	if (active) {
 		double2 v[8];
 		if constexpr (CL) {
-			const int s0 = s - (int) crank;
+			const int s0 = ((int) blockIdx.x - (int) crank) * CPB;
 			const double *xr = a.xin + (a.xin_map ? a.xin_map[s0] : s0);
 #pragma unroll
-			for (int i = 0; i < 2; ++i) {
-				const int n = (int) crank * (N / 8) + t + i * T;
+			for (int i = 0; i < NPC / THREADS; ++i) {
+				const int n = (int) crank * NPC + (int) threadIdx.x + i * THREADS;
 				const double *r0 = xr + 2L * n * a.xin_stride, *r1 = r0 + a.xin_stride;
 				const double2 a0 = *reinterpret_cast<const double2 *>(r0), a1 = *reinterpret_cast<const double2 *>(r0 + 2);
 				const double2 b0 = *reinterpret_cast<const double2 *>(r1), b1 = *reinterpret_cast<const double2 *>(r1 + 2);
@@ -491,11 +495,11 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 	if constexpr (CL) {
 		cg::cluster_group cluster = cg::this_cluster();
 		cluster.sync();   // all four channels' results are in their owners' buffers
-		const int s0 = s - (int) crank;
+		const int s0 = ((int) blockIdx.x - (int) crank) * CPB;
 		double *yr = a.yout + (a.yout_map ? a.yout_map[s0] : s0);
 #pragma unroll
-		for (int i = 0; i < 2; ++i) {
-			const int n = (int) crank * (N / 8) + t + i * T;
+		for (int i = 0; i < NPC / THREADS; ++i) {
+			const int n = (int) crank * NPC + (int) threadIdx.x + i * THREADS;
 			const double2 y0 = rbuf[0][spad(n)], y1 = rbuf[1][spad(n)], y2 = rbuf[2][spad(n)], y3 = rbuf[3][spad(n)];
 			double *r0 = yr + 2L * n * a.yout_stride, *r1 = r0 + a.yout_stride;
 			*reinterpret_cast<double2 *>(r0) = make_double2(y0.x, y1.x);
@@ -575,26 +579,38 @@ __global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
 	a.Y[(long) s * a.N + k] = make_double2((acc0.x + acc1.x) + (acc2.x + acc3.x), (acc0.y + acc1.y) + (acc2.y + acc3.y));
 }
 
-// Time-batched tail of the last level.  With V_j = sum_{p >= pf+T} X_{j-p} H_p (the part of block period j's
-// spectrum that only involves blocks at least pf+T periods old; pf = partitions summed inside the fused FFT
-// kernel), one launch after block q completes produces V_j for the T periods j = q+pf+1 .. q+pf+T at once: every
-// FDL row and every filter row is streamed ONCE for T outputs (the filter rows slide through a T-deep
+// Time-batched tail of the last level.  With V_j = sum_{p in [p_lo, p_hi)} X_{j-p} H_p, p_lo >= pf+T (the part of
+// block period j's spectrum that only involves blocks at least pf+T periods old; pf = partitions summed inside the
+// fused FFT kernel), one launch after block q completes produces V_j for the T periods j = q+pf+1 .. q+pf+T at once:
+// every FDL row and every filter row is streamed ONCE for T outputs (the filter rows slide through a T-deep
 // register window), instead of once per output.
-// Y_t[k] = sum_{m=pf+1}^{P-1} X_{q+pf+1-m}[k] * H_{m+t}[k] over the (m, t) with pf+T <= m+t < P.
+// V_t[k] = Vin_t[k] + sum_m X_{q+pf+1-m}[k] * H_{m+t}[k] over the (m, t) with p_lo <= m+t < p_hi.
+// Tiers: a deeper batch (larger T) may only take older partitions (p >= pf+T) but reads the filter less often; the
+// plan stacks two of them -- the far tier's result is the near tier's starting value `Vin`, the near tier's result
+// is what the per-block MAC starts from.
 struct MacBatchArgs {
 	const double2 *fdl;   // [s][P][N]
 	const double2 *H;     // [s][P][N] or [P][N]
 	double2 *V;           // [slot][s][N], slot = j mod n_slots
-	int N, P, n_sel;
+	int N, P, n_sel;      // P: rows of the FDL ring = partitions of the level
 	long q;               // block that just completed
 	int n_slots;
 	long h_ch_stride;
 	int pf;               // partitions 0..pf-1 are summed by the level's fused FFT kernel (1: upper levels, 2: level 0)
 	int s_first, s_step;  // channel of blockIdx.y: s_first + blockIdx.y * s_step (0, 1: all channels)
+	int p_lo, p_hi;       // partitions of this tier
+	const double2 *Vin;   // [slot][s][N], slot = j mod vin_slots: a farther tier's sums to start from (NULL: zero)
+	int vin_slots;
+};
+
+template <int T>
+struct MacBatchCfg {
+	static constexpr int THREADS = (T <= 8) ? 256 : 128;
+	static constexpr int MINB = (T <= 4) ? FIR_MAC_MINB : (T <= 8) ? 2 : (T <= 12) ? 3 : 2;
 };
 
 template <int T, bool SHARED_H>
-__global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_batch(MacBatchArgs a)
+__global__ void __launch_bounds__(MacBatchCfg<T>::THREADS, MacBatchCfg<T>::MINB) k_fir_mac_batch(MacBatchArgs a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = a.s_first + blockIdx.y * a.s_step;
@@ -603,13 +619,16 @@ __global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_ba
 	const bool dc = (k == 0);
 	const double2 zero = make_double2(0.0, 0.0);
 	double2 acc[T], hw[T];
-#define HROW(p) (((p) >= T + a.pf && (p) < a.P) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
+#define HROW(p) (((p) >= a.p_lo && (p) < a.p_hi) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
+	int m = a.p_lo - T + 1;   // first row that meets a partition of this tier: X_{q+pf+1-m} (m >= pf+1: it exists)
 #pragma unroll
 	for (int t = 0; t < T; ++t) {
-		acc[t] = zero;
-		hw[t] = HROW(a.pf + 1 + t);
+		const long j = a.q + a.pf + 1 + t;
+		acc[t] = a.Vin ? __ldcs(&a.Vin[((j % a.vin_slots) * a.n_sel + s) * (long) a.N + k]) : zero;
+		hw[t] = HROW(m + t);
 	}
-	int slot = (int) (a.q % a.P);   // row of X_{q+pf+1-m} for m = pf+1
+	int slot = (int) ((a.q + a.pf + 1 - m) % a.P);   // row of X_{q+pf+1-m}
+	if (slot < 0) slot += a.P;
 #define XROW(d) __ldcs(&fdl[(long) ((slot - (d) < 0) ? slot - (d) + a.P : slot - (d)) * a.N])
 #define STEP(XV, HN)                                                          \
 	do {                                                                      \
@@ -626,8 +645,7 @@ __global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_ba
 		_Pragma("unroll") for (int t = 0; t + 1 < T; ++t) hw[t] = hw[t + 1];  \
 		hw[T - 1] = HN;                                                       \
 	} while (0)
-	int m = a.pf + 1;
-	for (; m + 4 <= a.P; m += 4) {
+	for (; m + 4 <= a.p_hi; m += 4) {
 		// eight independent 16-byte loads in flight per thread, as in k_fir_mac
 		const double2 x0 = XROW(0), x1 = XROW(1), x2 = XROW(2), x3 = XROW(3);
 		const double2 h0 = HROW(m + T), h1 = HROW(m + T + 1), h2 = HROW(m + T + 2), h3 = HROW(m + T + 3);
@@ -638,7 +656,7 @@ __global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_ba
 		slot -= 4;
 		if (slot < 0) slot += a.P;
 	}
-	for (; m < a.P; ++m) {
+	for (; m < a.p_hi; ++m) {
 		const double2 x0 = XROW(0);
 		const double2 h0 = HROW(m + T);
 		STEP(x0, h0);
@@ -654,22 +672,29 @@ __global__ void __launch_bounds__(256, (T <= 4) ? FIR_MAC_MINB : 2) k_fir_mac_ba
 	}
 }
 
-constexpr int FIR_T_BATCH = 4;   // default batch depth; DSP_B200_FIR_T=6|8 selects the other instantiations
+constexpr int FIR_T_BATCH = 4;   // default depth of the near tier; DSP_B200_FIR_T=6|8 selects the other instantiations
+constexpr int FIR_T_FAR = 12;    // default depth of the far tier; DSP_B200_FIR_T2=0|8|12|16
 
-static void launch_mac_batch(int T, bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b)
+static bool batch_depth_ok(int T) { return T == 4 || T == 6 || T == 8 || T == 12 || T == 16; }
+static int batch_threads_for(int T) { return (T <= 8) ? 256 : 128; }
+
+template <int T>
+static void launch_mac_batch_t(bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b)
 {
-	ProfScope prof("fir_mac_batch", st);
-	if (T == 8) {
-		if (shared_h) LAUNCH((k_fir_mac_batch<8, true>), grid, threads, 0, st, b);
-		else LAUNCH((k_fir_mac_batch<8, false>), grid, threads, 0, st, b);
-	}
-	else if (T == 6) {
-		if (shared_h) LAUNCH((k_fir_mac_batch<6, true>), grid, threads, 0, st, b);
-		else LAUNCH((k_fir_mac_batch<6, false>), grid, threads, 0, st, b);
-	}
-	else {
-		if (shared_h) LAUNCH((k_fir_mac_batch<4, true>), grid, threads, 0, st, b);
-		else LAUNCH((k_fir_mac_batch<4, false>), grid, threads, 0, st, b);
+	if (shared_h) LAUNCH((k_fir_mac_batch<T, true>), grid, threads, 0, st, b);
+	else LAUNCH((k_fir_mac_batch<T, false>), grid, threads, 0, st, b);
+}
+
+// grid: x = N / threads, y = channels of this launch; `threads` at most batch_threads_for(T)
+static void launch_mac_batch(int T, bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b, const char *prof_name = "fir_mac_batch")
+{
+	ProfScope prof(prof_name, st);
+	switch (T) {
+	case 16: launch_mac_batch_t<16>(shared_h, grid, threads, st, b); break;
+	case 12: launch_mac_batch_t<12>(shared_h, grid, threads, st, b); break;
+	case 8: launch_mac_batch_t<8>(shared_h, grid, threads, st, b); break;
+	case 6: launch_mac_batch_t<6>(shared_h, grid, threads, st, b); break;
+	default: launch_mac_batch_t<4>(shared_h, grid, threads, st, b); break;
 	}
 }
 
@@ -832,7 +857,7 @@ static int configure_n()
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_inv<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
-		if constexpr (FftCfg<N>::CPB == 1) {
+		if constexpr (FftCfg<N>::CPB <= 2) {
 			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		}
@@ -867,13 +892,14 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 	if (configure_n<N>()) return -1;
 	if (a.n_ch <= 0) return 0;
 	ProfScope prof("fir_level0", st);
-	if constexpr (FftCfg<N>::CPB == 1) {
+	if constexpr (FftCfg<N>::CPB <= 2) {
 		if (a.cluster_io) {
+			constexpr int CPB = FftCfg<N>::CPB;
 			cudaLaunchConfig_t cfg = {};
-			cfg.gridDim = dim3(a.n_ch); cfg.blockDim = dim3(FftCfg<N>::THREADS); cfg.dynamicSmemBytes = FftCfg<N>::SMEM; cfg.stream = st;
+			cfg.gridDim = dim3(a.n_ch / CPB); cfg.blockDim = dim3(FftCfg<N>::THREADS); cfg.dynamicSmemBytes = FftCfg<N>::SMEM; cfg.stream = st;
 			cudaLaunchAttribute attr;
 			attr.id = cudaLaunchAttributeClusterDimension;
-			attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+			attr.val.clusterDim.x = 4 / CPB; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
 			cfg.attrs = &attr; cfg.numAttrs = 1;
 			if (a.P == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_fir_level0<N, 1, true>, a), return -1);
 			else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_fir_level0<N, 2, true>, a), return -1);
@@ -1051,6 +1077,15 @@ struct FirOp : Op {
 	double2 *d_V = nullptr;
 	cudaStream_t side2 = nullptr;
 	cudaEvent_t ev_batch[2] = { nullptr, nullptr };
+	// single-level plans: a second, deeper tier over the oldest partitions (its sums are the near tier's starting
+	// value), and the staggered schedule -- every block launches the tiers for the channels of one residue class
+	// (s mod T == block mod T) instead of all channels every T-th block, so that every block period carries the same work
+	int t_far = 0;
+	double2 *d_V2 = nullptr;             // far tier: V spectra for 2 t_far block periods
+	bool stagger = false;
+	cudaEvent_t ev_bs[8] = {};           // after the tier launches of a block (ring), ev_bs_last: the latest one
+	int ev_bs_n = 0;
+	cudaEvent_t ev_bs_last = nullptr;
 	cudaEvent_t ev_join[2] = { nullptr, nullptr };
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
@@ -1073,8 +1108,8 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}", t_batch, tail_pf, nb_max,
-		         use_pipe ? 1 : 0, pipe_pf);
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"stagger\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
+		         t_batch, t_far, stagger ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
 		return buf;
 	}
 
@@ -1092,6 +1127,8 @@ struct FirOp : Op {
 			side2 = nullptr;
 		}
 		for (cudaEvent_t &e : ev_batch) { if (e) cudaEventDestroy(e); e = nullptr; }
+		for (cudaEvent_t &e : ev_bs) { if (e) cudaEventDestroy(e); e = nullptr; }
+		ev_bs_last = nullptr; ev_bs_n = 0;
 		for (cudaEvent_t &e : ev_tail) { if (e) cudaEventDestroy(e); e = nullptr; }
 		for (cudaEvent_t &e : ev_join) { if (e) cudaEventDestroy(e); e = nullptr; }
 		if (ev_main) cudaEventDestroy(ev_main);
@@ -1102,9 +1139,9 @@ struct FirOp : Op {
 			lv[l] = FirLevel();
 		}
 		n_levels = 0;
-		dev_free(d_V); dev_free(d_Y_side); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
+		dev_free(d_V); dev_free(d_V2); dev_free(d_Y_side); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp); dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi); dev_free(d_stats);
-		d_V = d_Y_side = nullptr; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
+		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; stagger = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
 		d_Ybulk = nullptr; d_lo = d_hi = nullptr; d_stats = nullptr;
 		ltmp_cap = 0; tail_pf = 0; t_batch = 0; use_pipe = false; pipe_pf = 0; nb_max = 1;
 		urgent_pending = false; pre_valid = false; abs_pos = 0; planned = false;
@@ -1131,7 +1168,12 @@ struct FirOp : Op {
 		if (const char *e = getenv("DSP_B200_FIR_LEVEL_CAP")) cap = atol(e);
 		if (cap < B0) cap = B0;
 		if (cap > FIR_MAX_B) cap = FIR_MAX_B;
-		if (!multilevel || T <= 2L * B0 || B0 >= cap) {
+		// Blocks of 2048 frames stay a single level of 2048-frame partitions: with the two-tier batched tail it moves
+		// fewer bytes per sample than 2048 + 4096 (544 against 612 at 131072 taps) and every block period carries the
+		// same kernels (no upper-level kernel that has to land between two blocks)
+		long single_min = 2048;
+		if (const char *e = getenv("DSP_B200_FIR_SINGLE_MIN")) single_min = atol(e);
+		if (!multilevel || T <= 2L * B0 || B0 >= cap || B0 >= single_min) {
 			lv[0].B = B0; lv[0].tap0 = 0; lv[0].tap1 = T;
 			n_levels = 1;
 		}
@@ -1207,6 +1249,21 @@ struct FirOp : Op {
 						CUDA_TRY(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, lo), return -1);
 						CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[0], cudaEventDisableTiming), return -1);
 						CUDA_TRY(cudaEventCreateWithFlags(&ev_batch[1], cudaEventDisableTiming), return -1);
+					}
+					if (!use_pipe && pf == 2) {
+						// far tier: partitions >= t_far + 2, T = t_far periods per launch; only when the level is long
+						// enough for it to pay (the near tier keeps partitions t_batch + 2 .. t_far + 1)
+						int t2 = FIR_T_FAR;
+						if (const char *e = getenv("DSP_B200_FIR_T2")) t2 = atoi(e);
+						if (!batch_depth_ok(t2) || t2 <= t_batch || t2 % t_batch != 0 || L.P < 2 * t2 + pf) t2 = 0;
+						if (t2 > 0) {
+							t_far = t2;
+							d_V2 = dev_alloc<double2>((size_t) 2 * t_far * n_sel * L.B);
+							if (!d_V2) return -1;
+						}
+						const char *sg = getenv("DSP_B200_FIR_STAGGER");
+						stagger = !(sg && sg[0] == '0');
+						for (cudaEvent_t &e : ev_bs) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return -1);
 					}
 				}
 				if (use_pipe) {
@@ -1290,6 +1347,8 @@ struct FirOp : Op {
 		if (side) cudaStreamSynchronize(side);
 		if (side2) cudaStreamSynchronize(side2);
 		if (d_V) cudaMemsetAsync(d_V, 0, (size_t) 2 * t_batch * n_sel * lv[n_levels - 1].B * sizeof(double2), st);
+		if (d_V2) cudaMemsetAsync(d_V2, 0, (size_t) 2 * t_far * n_sel * lv[n_levels - 1].B * sizeof(double2), st);
+		ev_bs_last = nullptr;
 		for (int l = 0; l < n_levels; ++l) {
 			FirLevel &L = lv[l];
 			L.blk = 0;
@@ -1388,6 +1447,7 @@ struct FirOp : Op {
 				b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
 				b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 				b.pf = 1;
+				b.p_lo = t_batch + 1; b.p_hi = L.P;
 				b.s_first = 0; b.s_step = 1;
 				const int threads = (L.B < 256) ? L.B : 256;
 				dim3 grid(L.B / threads, n_sel);
@@ -1424,6 +1484,7 @@ struct FirOp : Op {
 					b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q - 1; b.n_slots = 2 * t_batch;
 					b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
 					b.pf = 2;
+					b.p_lo = t_batch + 2; b.p_hi = L.P;
 					b.s_first = g; b.s_step = t_batch;
 					const int threads = (L.B < 256) ? L.B : 256;
 					dim3 grid(L.B / threads, (n_sel - g + t_batch - 1) / t_batch);
@@ -1438,45 +1499,62 @@ struct FirOp : Op {
 			if (!on_main) CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
 		}
 		if (t_batch > 0) {
-			const int T = t_batch;
-			if (j >= 3) {
-				const long qb = ((j - 3) / T) * T;   // V_j comes from the batch launched after block qb
-				CUDA_TRY(cudaStreamWaitEvent(ts, ev_batch[(qb / T) & 1], 0), return -1);
-			}
-			mac(L, 2, T + 2, j, ts, Y, d_V + (size_t) (j % (2 * T)) * n_sel * L.B);
+			// V_j is complete once every tier launch up to block q-1 is (one stream, in order)
+			if (ev_bs_last) CUDA_TRY(cudaStreamWaitEvent(ts, ev_bs_last, 0), return -1);
+			mac(L, 2, t_batch + 2, j, ts, Y, d_V + (size_t) (j % (2 * t_batch)) * n_sel * L.B);
 		}
 		else mac(L, 2, L.P, j, ts, Y);
 		CUDA_TRY(cudaEventRecord(ev_tail[j & 1], ts), return -1);
-		if (t_batch > 0 && q % t_batch == 0) {
-			if (!serial) CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
-			if (launch_batch0(L, q, bs)) return -1;
+		if (t_batch > 0 && launch_tiers0(L, q, bs, serial)) return -1;
+		return 0;
+	}
+
+	// Tier launches after block q of a single-level plan (far tier first: the near tier starts from its sums).  A tier
+	// of depth T produces V_j = (farther tier's V_j) + sum_{p in tier} X_{j-p} H_p for the T periods j = q+3 .. q+2+T
+	// from the blocks up to q.  Staggered: for the channels s with s mod T == q mod T, every block; otherwise for all
+	// channels when q mod T == 0.  Both ways a channel's periods j are covered exactly once, and the near tier's
+	// window of a channel lies inside one far window of that channel (t_far is a multiple of t_batch, the far launch
+	// of the same block comes first).
+	int launch_tiers0(FirLevel &L, long q, cudaStream_t bs, bool serial)
+	{
+		bool any = false;
+		for (int i = (t_far > 0) ? 1 : 0; i >= 0; --i) {
+			const int T = i ? t_far : t_batch;
+			const int g = (int) (q % T);
+			if (!stagger && g != 0) continue;
+			if (stagger && n_sel <= g) continue;
+			if (!any && !serial) CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
+			any = true;
+			MacBatchArgs b = {};
+			b.fdl = L.fdl; b.H = L.H; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q;
+			b.V = i ? d_V2 : d_V; b.n_slots = 2 * T;
+			b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+			b.pf = 2;
+			b.p_lo = T + 2; b.p_hi = (i == 0 && t_far > 0) ? t_far + 2 : L.P;
+			if (i == 0 && t_far > 0) { b.Vin = d_V2; b.vin_slots = 2 * t_far; }
+			b.s_first = stagger ? g : 0; b.s_step = stagger ? T : 1;
+			int threads = batch_threads_for(T);
+			if ((batch_threads == 128 || batch_threads == 64) && batch_threads < threads) threads = batch_threads;
+			if (L.B < threads) threads = L.B;
+			dim3 grid(L.B / threads, stagger ? (n_sel - g + T - 1) / T : n_sel);
+			launch_mac_batch(T, fc == 1, grid, threads, bs, b, i ? "fir_mac_batch_far" : "fir_mac_batch");
+		}
+		if (any) {
+			cudaEvent_t e = ev_bs[ev_bs_n++ & 7];
+			CUDA_TRY(cudaEventRecord(e, bs), return -1);
+			ev_bs_last = e;
 		}
 		return 0;
 	}
 
-	// V_j = sum_{p >= 2+T} X_{j-p} H_p for the T periods j = q+3 .. q+2+T, from the blocks up to q (level 0 of a single-level plan)
-	int launch_batch0(FirLevel &L, long q, cudaStream_t bs)
-	{
-		MacBatchArgs b = {};
-		b.fdl = L.fdl; b.H = L.H; b.V = d_V; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q; b.n_slots = 2 * t_batch;
-		b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
-		b.pf = 2;
-		b.s_first = 0; b.s_step = 1;
-		int threads = (batch_threads == 128 || batch_threads == 64) ? batch_threads : 256;
-		if (L.B < threads) threads = L.B;
-		dim3 grid(L.B / threads, n_sel);
-		launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
-		CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
-		return 0;
-	}
-
-	// The main stream may only go on with block `blk` of a single-level tail plan once the batch that produced V_blk
-	// is complete: the pipeline kernel reads V_blk, and every path overwrites FDL row blk % P, which that batch
-	// (launched after block T*floor((blk-3)/T)) still reads until then.
+	// The main stream may only go on with block `blk` of a single-level tail plan once the tier launches that read FDL
+	// row blk % P (those after the blocks up to blk-4) are complete.  The fused kernel's path gets that from waiting
+	// for Y_blk (whose MAC waited for the launches up to blk-3); the general path waits here, for all of them.
 	int wait_batch_for(long blk, cudaStream_t st)
 	{
-		if (t_batch > 0 && tail_pf == 2 && !use_pipe && blk >= 3 && !g_fir_serialize.load(std::memory_order_relaxed))
-			CUDA_TRY(cudaStreamWaitEvent(st, ev_batch[((blk - 3) / t_batch) & 1], 0), return -1);
+		(void) blk;
+		if (t_batch > 0 && tail_pf == 2 && !use_pipe && ev_bs_last && !g_fir_serialize.load(std::memory_order_relaxed))
+			CUDA_TRY(cudaStreamWaitEvent(st, ev_bs_last, 0), return -1);
 		return 0;
 	}
 
@@ -1700,7 +1778,7 @@ struct FirOp : Op {
 						f.xin = src; f.xin_stride = C; f.xin_map = d_ch_map;
 						f.yout = d; f.yout_stride = dstride; f.yout_map = dmap;
 						// four adjacent channels per cluster: needs the selected channels contiguous and 16-byte aligned rows
-						f.cluster_io = cluster_ok && B0 >= 4096 && C % 2 == 0 && dstride % 2 == 0 &&
+						f.cluster_io = cluster_ok && B0 >= 2048 && C % 2 == 0 && dstride % 2 == 0 &&
 						               ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d)) & 15) == 0;
 					}
 					f.fdl = L0.fdl; f.fdl_ch_stride = (long) L0.R * B0; f.fdl_rows = L0.R;

@@ -3,12 +3,13 @@
 (gpurun_out/prof_fir_step.ncu-rep, see scripts/gpu_round.sh): DRAM bytes (read + write) per launch of each
 kernel, times its launches per step as counted in the same capture window.
 
-    python scripts/traffic_from_ncu.py [C F taps h]      # defaults: 256 4096 131072 1
+    python scripts/traffic_from_ncu.py [C F taps h [far]]      # defaults: 256 4096 131072 1 12 (far: depth of the far batch tier)
 """
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = os.path.join(ROOT, "gpurun_out", os.environ.get("NCU_REP", "prof_fir_step.ncu-rep"))
 C, F, taps, h = (int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (256, 4096, 131072, 1)))
+far = int(sys.argv[5]) if len(sys.argv) >= 6 else 12
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
@@ -33,6 +34,6 @@ out["dram_bytes_per_step"] = total
 out["source"] = "ncu --set full --clock-control none -k regex:k_fir_ (gpurun_out/prof_fir_step.ncu-rep); dram__bytes_read.sum + dram__bytes_write.sum"
 path = os.path.join(ROOT, "profiles", "traffic.json")
 tr = json.load(open(path)) if os.path.exists(path) else {}
-tr["step:C%d:F%d:taps%d:h%d:pipe%d" % (C, F, taps, h, 1 if pipe else 0)] = out
+tr["step:C%d:F%d:taps%d:h%d:pipe%d:far%d" % (C, F, taps, h, 1 if pipe else 0, 0 if pipe else far)] = out
 json.dump(tr, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -41,11 +41,18 @@ def write_ir(tmp_path, h):
     return p
 
 
-@pytest.mark.parametrize("variant", ["pipe_t4", "legacy_t4", "legacy_t6", "legacy_t8"])
+# <path>_t<near depth>[_f<far depth>][_u]: _u = every tier for all channels every T-th block instead of one residue
+# class of channels per block; no _f = the default far tier (12)
+VARIANTS = ["pipe_t4", "legacy_t4", "legacy_t4_f0_u", "legacy_t4_f0", "legacy_t4_f8", "legacy_t4_f12_u", "legacy_t6_f12", "legacy_t6_f0_u",
+            "legacy_t8_f0_u", "legacy_t8_f0"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_path, variant):
     """8 contiguous channels (a multiple of 4: the cluster form of the pre-pipeline kernel is taken too), per-channel
-    131072-tap IRs, 48 random blocks of 4096 frames: partitions up to p = 31 all meet non-zero blocks and 10+ batched
-    V spectra are consumed.  Reference = fir_p.c compiled unmodified (its own 32/256/4096 partition plan)."""
+    131072-tap IRs, 48 random blocks of 4096 frames: partitions up to p = 31 all meet non-zero blocks, 10+ batched
+    V spectra of the near tier and 3 windows of the far tier are consumed.  Reference = fir_p.c compiled unmodified
+    (its own 32/256/4096 partition plan)."""
     from oracle import restate
     fs, C, taps, F, nblk = 48000, 8, 131072, 4096, 48
     h = np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
@@ -58,14 +65,20 @@ def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_
         r.close()
     else:
         want = restate.fir_stream(x, h)
-    pipe, t = variant.split("_t")
-    with env(DSP_B200_FIR_PIPE="1" if pipe == "pipe" else "0", DSP_B200_FIR_T=t):
+    parts = variant.split("_")
+    pipe, t = parts[0], parts[1][1:]
+    far = next((q[1:] for q in parts[2:] if q[0] == "f"), None)
+    unstaggered = "u" in parts[2:]
+    with env(DSP_B200_FIR_PIPE="1" if pipe == "pipe" else "0", DSP_B200_FIR_T=t, DSP_B200_FIR_T2=far,
+             DSP_B200_FIR_STAGGER="0" if unstaggered else None):
         ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
         plan = ch.describe()[0]
     assert plan["levels"] == [{"B": 4096, "P": 32}] and plan["t_batch"] == int(t), plan
     assert plan["pipe"] == (1 if pipe == "pipe" else 0), plan
     if pipe == "pipe":
-        assert plan["pipe_pf"] == int(t) + 2, plan
+        assert plan["pipe_pf"] == int(t) + 2 and plan["t_far"] == 0, plan
+    else:
+        assert plan["t_far"] == (12 if far is None else int(far)) and plan["stagger"] == (0 if unstaggered else 1), plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, nblk * F, F)])
     ch.close()
     assert got.shape == want.shape
@@ -108,13 +121,13 @@ def test_pipe_more_channels_than_sms(gpu_lib, taps, shared, pipe):
         assert np.array_equal(got[:, 0], got[:, 40]) and np.array_equal(got[:, 3], got[:, 203])
 
 
-@pytest.mark.parametrize("pipe", [1, 0])
-def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe):
-    """The pipeline kernel behind a scattered selector, writing into the compact buffer of fir's latency ring, with
-    whole blocks and ragged calls alternating on the same state (general path <-> pipeline kernel, batched V kept
-    current by both)."""
+@pytest.mark.parametrize("pipe,taps", [(1, 60000), (0, 60000), (0, 120000)])
+def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe, taps):
+    """The block kernel behind a scattered selector, writing into the compact buffer of fir's latency ring, with
+    whole blocks and ragged calls alternating on the same state (general path <-> fused / pipeline kernel, batched V kept
+    current by both).  120000 taps = 30 partitions: both tiers of the batched tail."""
     from oracle import restate
-    fs, C, F, taps = 48000, 10, 4096, 60000
+    fs, C, F = 48000, 10, 4096
     rng = np.random.default_rng(77)
     sel = [c in (0, 2, 3, 4, 7, 9) for c in range(C)]
     h = np.stack([restate.bench_ir(taps, c) for c in range(sum(sel))], axis=1)
@@ -125,7 +138,7 @@ def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe):
         with env(DSP_B200_FIR_PIPE=pipe):
             ch = gpu_lib.Chain(fs, C).add_fir(h, selector=sel, latency=lat, block_hint=F)
             plan = ch.describe()[0]
-        assert plan["pipe"] == pipe and plan["t_batch"] == 4, plan
+        assert plan["pipe"] == pipe and plan["t_batch"] == 4 and plan["t_far"] == (12 if taps > 100000 else 0), plan
         cuts = [0, F, 2 * F, 2 * F + 100, 3 * F, 4 * F, 5 * F, 6 * F, 7 * F, 7 * F + 1, 8 * F - 1, 8 * F, 9 * F, 10 * F, 11 * F, 12 * F,
                 12 * F + 2000, 14 * F, 15 * F, 16 * F, 17 * F, 18 * F, 19 * F, 20 * F, 21 * F, 22 * F, N]
         got = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
@@ -140,22 +153,44 @@ def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe):
         ch.close()
 
 
-@pytest.mark.parametrize("taps", [20000, 70000])
-def test_pipe_2048_frame_partitions(gpu_lib, taps):
-    """The 2048-point instantiation of the pipeline kernel (DSP_B200_FIR_LEVEL_CAP=2048 keeps a single level of
-    2048-frame partitions: 10 and 35 partitions)."""
+@pytest.mark.parametrize("taps,pipe,far", [(20000, 1, None), (70000, 1, None), (20000, 0, None), (70000, 0, None), (140000, 0, 16), (140000, 0, 8)])
+def test_2048_frame_partitions(gpu_lib, taps, pipe, far):
+    """Blocks of 2048 frames (the CLI default): a single level of 2048-frame partitions -- 10, 35 and 69 of them --
+    through the fused kernel's two-CTA cluster form + MAC + two batch tiers (far tier of 12 by default, 16 and 8 on
+    request), and through the 2048-point instantiation of the pipeline kernel.  8 channels: two clusters."""
     from oracle import restate
-    fs, C, F = 48000, 5, 2048
+    fs, C, F = 48000, 8, 2048
     rng = np.random.default_rng(taps)
     h = np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
-    N = 40 * F
+    N = (40 if taps < 100000 else 90) * F
     x = rng.standard_normal((N, C)) * 0.2
     want = restate.fir_stream(x, h)
-    with env(DSP_B200_FIR_LEVEL_CAP="2048", DSP_B200_FIR_PIPE=1):
+    with env(DSP_B200_FIR_PIPE=pipe, DSP_B200_FIR_T2=far):
         ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
         plan = ch.describe()[0]
-    assert plan["pipe"] == 1 and plan["levels"][0]["B"] == 2048 and len(plan["levels"]) == 1, plan
+    assert plan["pipe"] == pipe and plan["levels"][0]["B"] == 2048 and len(plan["levels"]) == 1, plan
+    if not pipe:
+        P = plan["levels"][0]["P"]
+        assert plan["t_far"] == ((far or 12) if P >= 2 * (far or 12) + 2 else 0) and plan["stagger"] == 1, plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, N, F)])
+    ch.close()
+    assert rms(got - want) <= RMS_TOL, rms(got - want)
+
+
+def test_2048_frame_blocks_two_levels_on_request(gpu_lib):
+    """DSP_B200_FIR_SINGLE_MIN=4096 brings back the 2048 + 4096 plan (upper level on the side stream, its tail
+    time-batched there)."""
+    from oracle import restate
+    fs, C, F, taps = 48000, 4, 2048, 70000
+    rng = np.random.default_rng(5)
+    h = np.stack([restate.bench_ir(taps, c) for c in range(C)], axis=1)
+    x = rng.standard_normal((40 * F, C)) * 0.2
+    want = restate.fir_stream(x, h)
+    with env(DSP_B200_FIR_SINGLE_MIN="4096"):
+        ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
+        plan = ch.describe()[0]
+    assert [L["B"] for L in plan["levels"]] == [2048, 4096] and plan["tail_pf"] == 1 and plan["t_batch"] == 4, plan
+    got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, 40 * F, F)])
     ch.close()
     assert rms(got - want) <= RMS_TOL, rms(got - want)
 

@@ -322,9 +322,10 @@ def test_fir_p_bulk_form_mixes_with_ragged_calls(gpu_lib, shared):
     ch.close()
 
 
-@pytest.mark.parametrize("block,taps,shared", [(4096, 60000, True), (4096, 131072, False), (8192, 100000, False), (4096, 13000, True)])
+@pytest.mark.parametrize("block,taps,shared", [(4096, 60000, True), (4096, 131072, False), (8192, 100000, False), (4096, 13000, True),
+                                               (2048, 131072, False), (2048, 40000, True)])
 def test_fir_p_single_level_with_tail(gpu_lib, block, taps, shared):
-    """Blocks of the largest partition size the planner uses (4096; or the block itself above that): ONE level,
+    """Blocks of 2048 frames and up (4096 is the largest partition size of multi-level plans): ONE level,
     its fused kernel sums partitions 0 and 1, the rest arrives as a spectrum accumulated two blocks ahead
     (time-batched when there are enough partitions; 13000 taps = 4 partitions: not batched).  Aligned calls,
     then the same stream in random cuts (general path and fused path interleave on the same state)."""
