@@ -527,8 +527,11 @@ struct MacArgs {
 #ifndef FIR_MAC_MINB
 #define FIR_MAC_MINB 3
 #endif
-template <bool SHARED_H>
-__global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
+// Bin 0 of a row is packed (DC and Nyquist, both real: two real products instead of a complex one).  Only the warp
+// that holds it compiles the special case (DCW); everywhere else the inner loop is the plain complex MAC, without
+// predicated-off copies of every FMA.
+template <bool SHARED_H, bool DCW>
+__device__ __forceinline__ void fir_mac_body(const MacArgs &a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = blockIdx.y;
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
 	double2 acc0 = a.init ? __ldcs(&a.init[(long) s * a.N + k]) : make_double2(0.0, 0.0);
 	double2 acc1 = make_double2(0.0, 0.0), acc2 = acc1, acc3 = acc1;
-	const bool dc = (k == 0);
+	const bool dc = DCW && (k == 0);
 	int slot = a.slot0 - a.p0;
 	slot %= a.P;
 	if (slot < 0) slot += a.P;
@@ -579,6 +582,13 @@ __global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
 	a.Y[(long) s * a.N + k] = make_double2((acc0.x + acc1.x) + (acc2.x + acc3.x), (acc0.y + acc1.y) + (acc2.y + acc3.y));
 }
 
+template <bool SHARED_H>
+__global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
+{
+	if (blockIdx.x == 0 && threadIdx.x < 32) fir_mac_body<SHARED_H, true>(a);
+	else fir_mac_body<SHARED_H, false>(a);
+}
+
 // Time-batched tail of the last level.  With V_j = sum_{p in [p_lo, p_hi)} X_{j-p} H_p, p_lo >= pf+T (the part of
 // block period j's spectrum that only involves blocks at least pf+T periods old; pf = partitions summed inside the
 // fused FFT kernel), one launch after block q completes produces V_j for the T periods j = q+pf+1 .. q+pf+T at once:
@@ -609,14 +619,14 @@ struct MacBatchCfg {
 	static constexpr int MINB = (T <= 4) ? FIR_MAC_MINB : (T <= 8) ? 2 : (T <= 12) ? 3 : 2;
 };
 
-template <int T, bool SHARED_H>
-__global__ void __launch_bounds__(MacBatchCfg<T>::THREADS, MacBatchCfg<T>::MINB) k_fir_mac_batch(MacBatchArgs a)
+template <int T, bool SHARED_H, bool DCW>
+__device__ __forceinline__ void fir_mac_batch_body(const MacBatchArgs &a)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = a.s_first + blockIdx.y * a.s_step;
 	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
-	const bool dc = (k == 0);
+	const bool dc = DCW && (k == 0);
 	const double2 zero = make_double2(0.0, 0.0);
 	double2 acc[T], hw[T];
 #define HROW(p) (((p) >= a.p_lo && (p) < a.p_hi) ? (SHARED_H ? __ldg(&H[(long) (p) * a.N]) : __ldcs(&H[(long) (p) * a.N])) : zero)
@@ -670,6 +680,13 @@ __global__ void __launch_bounds__(MacBatchCfg<T>::THREADS, MacBatchCfg<T>::MINB)
 		const long j = a.q + a.pf + 1 + t;
 		a.V[((j % a.n_slots) * a.n_sel + s) * (long) a.N + k] = acc[t];
 	}
+}
+
+template <int T, bool SHARED_H>
+__global__ void __launch_bounds__(MacBatchCfg<T>::THREADS, MacBatchCfg<T>::MINB) k_fir_mac_batch(MacBatchArgs a)
+{
+	if (blockIdx.x == 0 && threadIdx.x < 32) fir_mac_batch_body<T, SHARED_H, true>(a);   // the warp that holds the packed bin 0
+	else fir_mac_batch_body<T, SHARED_H, false>(a);
 }
 
 constexpr int FIR_T_BATCH = 4;   // default depth of the near tier; DSP_B200_FIR_T=6|8 selects the other instantiations
@@ -846,6 +863,18 @@ __global__ void k_delay_write(const double *y, long y_stride, double *ring, int 
 // ------------------------------------------------------------------------------------------
 // launch helpers (dispatch on the FFT size)
 // ------------------------------------------------------------------------------------------
+// Dynamic shared memory of the fused block kernel: what the transform buffers need, or more on request
+// (DSP_B200_FIR_L0_SMEM_KB: a way to cap its CTAs per SM, so that the streaming kernels of the other streams find
+// registers next to it)
+template <int N>
+static size_t level0_smem()
+{
+	static const long want = getenv("DSP_B200_FIR_L0_SMEM_KB") ? atol(getenv("DSP_B200_FIR_L0_SMEM_KB")) * 1024 : 0;
+	size_t n = FftCfg<N>::SMEM;
+	if (N >= 2048 && want > (long) n) n = (size_t) ((want > 227 * 1024) ? 227 * 1024 : want);
+	return n;
+}
+
 template <int N>
 static int configure_n()
 {
@@ -855,11 +884,11 @@ static int configure_n()
 	if (!configured[dev & 63].load()) {
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_fwd<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
 		CUDA_TRY(cudaFuncSetAttribute(k_fir_inv<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
-		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
-		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
+		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
+		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
 		if constexpr (FftCfg<N>::CPB <= 2) {
-			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
-			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<N>::SMEM), return -1);
+			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
+			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
 		}
 		configured[dev & 63].store(1);
 	}
@@ -896,7 +925,7 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 		if (a.cluster_io) {
 			constexpr int CPB = FftCfg<N>::CPB;
 			cudaLaunchConfig_t cfg = {};
-			cfg.gridDim = dim3(a.n_ch / CPB); cfg.blockDim = dim3(FftCfg<N>::THREADS); cfg.dynamicSmemBytes = FftCfg<N>::SMEM; cfg.stream = st;
+			cfg.gridDim = dim3(a.n_ch / CPB); cfg.blockDim = dim3(FftCfg<N>::THREADS); cfg.dynamicSmemBytes = level0_smem<N>(); cfg.stream = st;
 			cudaLaunchAttribute attr;
 			attr.id = cudaLaunchAttributeClusterDimension;
 			attr.val.clusterDim.x = 4 / CPB; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
@@ -907,8 +936,8 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 			return 0;
 		}
 	}
-	if (a.P == 1) LAUNCH((k_fir_level0<N, 1>), ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
-	else LAUNCH((k_fir_level0<N, 2>), ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, FftCfg<N>::SMEM, st, a);
+	if (a.P == 1) LAUNCH((k_fir_level0<N, 1>), ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, level0_smem<N>(), st, a);
+	else LAUNCH((k_fir_level0<N, 2>), ceil_div(a.n_ch, FftCfg<N>::CPB), FftCfg<N>::THREADS, level0_smem<N>(), st, a);
 	return 0;
 }
 
@@ -968,7 +997,9 @@ static int launch_level0(int N, const L0Args &a, cudaStream_t st) { DISPATCH_N(N
 static void launch_mac(const MacArgs &a, int n_sel, bool shared_h, const char *prof_name, cudaStream_t st)
 {
 	if (n_sel <= 0) return;
-	const int threads = (a.N < 256) ? a.N : 256;
+	static const int want = getenv("DSP_B200_FIR_MAC_THREADS") ? atoi(getenv("DSP_B200_FIR_MAC_THREADS")) : 256;
+	int threads = (want == 128 || want == 64) ? want : 256;
+	if (a.N < threads) threads = a.N;
 	dim3 grid(a.N / threads, n_sel);
 	ProfScope prof(prof_name, st);
 	if (shared_h) LAUNCH(k_fir_mac<true>, grid, threads, 0, st, a);
