@@ -613,10 +613,19 @@ struct MacBatchArgs {
 	int vin_slots;
 };
 
+#ifndef FIR_BATCH_PREFETCH
+#define FIR_BATCH_PREFETCH 0
+#endif
 template <int T>
 struct MacBatchCfg {
+#if FIR_BATCH_PREFETCH
+	// software-pipelined form: eight more 16-byte registers per thread (the next four rows of X and H in flight)
+	static constexpr int THREADS = (T <= 4) ? 256 : 128;
+	static constexpr int MINB = (T <= 4) ? 2 : (T <= 8) ? 3 : 2;
+#else
 	static constexpr int THREADS = (T <= 8) ? 256 : 128;
 	static constexpr int MINB = (T <= 4) ? FIR_MAC_MINB : (T <= 8) ? 2 : (T <= 12) ? 3 : 2;
+#endif
 };
 
 template <int T, bool SHARED_H, bool DCW>
@@ -655,6 +664,26 @@ __device__ __forceinline__ void fir_mac_batch_body(const MacBatchArgs &a)
 		_Pragma("unroll") for (int t = 0; t + 1 < T; ++t) hw[t] = hw[t + 1];  \
 		hw[T - 1] = HN;                                                       \
 	} while (0)
+#if FIR_BATCH_PREFETCH
+	// the eight loads of the NEXT four rows are issued before the current four are used; rows past the tier are zeros
+#define XROWG(mm, d) (((mm) + (d) < a.p_hi) ? XROW(d) : zero)
+	double2 x0 = XROWG(m, 0), x1 = XROWG(m, 1), x2 = XROWG(m, 2), x3 = XROWG(m, 3);
+	double2 h0 = HROW(m + T), h1 = HROW(m + T + 1), h2 = HROW(m + T + 2), h3 = HROW(m + T + 3);
+	for (; m < a.p_hi; m += 4) {
+		slot -= 4;
+		if (slot < 0) slot += a.P;
+		const int mn = m + 4;
+		const double2 nx0 = XROWG(mn, 0), nx1 = XROWG(mn, 1), nx2 = XROWG(mn, 2), nx3 = XROWG(mn, 3);
+		const double2 nh0 = HROW(mn + T), nh1 = HROW(mn + T + 1), nh2 = HROW(mn + T + 2), nh3 = HROW(mn + T + 3);
+		STEP(x0, h0);
+		STEP(x1, h1);
+		STEP(x2, h2);
+		STEP(x3, h3);
+		x0 = nx0; x1 = nx1; x2 = nx2; x3 = nx3;
+		h0 = nh0; h1 = nh1; h2 = nh2; h3 = nh3;
+	}
+#undef XROWG
+#else
 	for (; m + 4 <= a.p_hi; m += 4) {
 		// eight independent 16-byte loads in flight per thread, as in k_fir_mac
 		const double2 x0 = XROW(0), x1 = XROW(1), x2 = XROW(2), x3 = XROW(3);
@@ -672,6 +701,7 @@ __device__ __forceinline__ void fir_mac_batch_body(const MacBatchArgs &a)
 		STEP(x0, h0);
 		slot = (slot == 0) ? a.P - 1 : slot - 1;
 	}
+#endif
 #undef XROW
 #undef STEP
 #undef HROW
@@ -693,7 +723,11 @@ constexpr int FIR_T_BATCH = 4;   // default depth of the near tier; DSP_B200_FIR
 constexpr int FIR_T_FAR = 12;    // default depth of the far tier; DSP_B200_FIR_T2=0|8|12|16
 
 static bool batch_depth_ok(int T) { return T == 4 || T == 6 || T == 8 || T == 12 || T == 16; }
-static int batch_threads_for(int T) { return (T <= 8) ? 256 : 128; }
+static int batch_threads_for(int T)
+{
+	return (T == 16) ? MacBatchCfg<16>::THREADS : (T == 12) ? MacBatchCfg<12>::THREADS : (T == 8) ? MacBatchCfg<8>::THREADS
+	     : (T == 6) ? MacBatchCfg<6>::THREADS : MacBatchCfg<4>::THREADS;
+}
 
 template <int T>
 static void launch_mac_batch_t(bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b)
@@ -1480,7 +1514,7 @@ struct FirOp : Op {
 				b.pf = 1;
 				b.p_lo = t_batch + 1; b.p_hi = L.P;
 				b.s_first = 0; b.s_step = 1;
-				const int threads = (L.B < 256) ? L.B : 256;
+				const int threads = (L.B < batch_threads_for(t_batch)) ? L.B : batch_threads_for(t_batch);
 				dim3 grid(L.B / threads, n_sel);
 				launch_mac_batch(t_batch, fc == 1, grid, threads, bs, b);
 				CUDA_TRY(cudaEventRecord(ev_batch[(q / t_batch) & 1], bs), return -1);
@@ -1517,7 +1551,7 @@ struct FirOp : Op {
 					b.pf = 2;
 					b.p_lo = t_batch + 2; b.p_hi = L.P;
 					b.s_first = g; b.s_step = t_batch;
-					const int threads = (L.B < 256) ? L.B : 256;
+					const int threads = (L.B < batch_threads_for(t_batch)) ? L.B : batch_threads_for(t_batch);
 					dim3 grid(L.B / threads, (n_sel - g + t_batch - 1) / t_batch);
 					launch_mac_batch(t_batch, fc == 1, grid, threads, st, b);
 				}
