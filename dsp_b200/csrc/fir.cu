@@ -303,6 +303,63 @@ __device__ __forceinline__ void prefetch_rows(const void *p, long bytes, int t, 
 	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) prefetch_l2(c + off);
 }
 
+// FIR_L0_ASYNC (default): the cluster form of the fused kernel moves its samples between the CTAs of a cluster with
+// st.async -- remote shared-memory stores that complete bytes on the RECEIVER's mbarrier -- instead of plain
+// distributed-shared-memory stores fenced by cluster.sync().  The releasing cluster barrier compiles to MEMBAR.ALL.GPU
+// (+ ERRBAR): every thread waits for all its global stores and prefetches in flight, four times per block; a third of
+// the kernel's stall samples were that wait (profiles/r02_prof_fir_step_*).  With st.async nobody fences: a CTA
+// waits on its own mbarrier until the bytes addressed to it have landed.
+#ifndef FIR_L0_ASYNC
+#define FIR_L0_ASYNC 1
+#endif
+
+template <int N>
+struct L0ClCfg {
+	static constexpr int CPB = FftCfg<N>::CPB;
+	static constexpr int NCL = (CPB <= 2) ? 4 / CPB : 1;   // CTAs per cluster
+	static constexpr int NPC = N / 2 / NCL;                // packed frame pairs a CTA moves for all four channels
+	// after the transform buffers: result staging [4 channels][NPC] and two mbarriers (samples in, results in)
+	static constexpr size_t STAGE_BYTES = (size_t) 4 * NPC * sizeof(double2);
+	static constexpr size_t SMEM = FIR_L0_ASYNC ? FftCfg<N>::SMEM + STAGE_BYTES + 16 : FftCfg<N>::SMEM;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank)
+{
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+	return r;
+}
+
+// 16 bytes into the shared memory of a CTA of the cluster; the bytes count on that CTA's mbarrier when they have landed
+__device__ __forceinline__ void st_async_f64x2(uint32_t dst, double x, double y, uint32_t mbar)
+{
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst), "d"(x), "d"(y), "r"(mbar)
+	             : "memory");
+}
+
+// wait for a phase completed by other CTAs' st.async (acquire at cluster scope); traps instead of hanging
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, unsigned parity)
+{
+	unsigned spins = 0;
+	for (;;) {
+		uint32_t ok;
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok)
+		             : "r"(smem_u32(bar)), "r"(parity)
+		             : "memory");
+		if (ok) return;
+		if (++spins > (1u << 20)) __trap();
+	}
+}
+
+// Cluster-wide execution barrier WITHOUT the release fence of cluster.sync(): for points where nothing written before
+// has to become visible to the other CTAs (the fence of the releasing form waits for every global store and prefetch
+// the thread still has in flight -- a third of the fused kernel's stall samples were that wait).
+__device__ __forceinline__ void cluster_barrier_relaxed()
+{
+	asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 h)
 {
 	return make_double2(fma(x.x, h.x, fma(-x.y, h.y, acc.x)), fma(x.x, h.y, fma(x.y, h.x, acc.y)));
@@ -332,6 +389,22 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 	double2 *buf = smem + (size_t) g * FftCfg<N>::STRIDE;
 	namespace cg = cooperative_groups;
 	unsigned crank = 0;
+#if FIR_L0_ASYNC
+	double2 *stage = reinterpret_cast<double2 *>(reinterpret_cast<char *>(smem) + FftCfg<N>::SMEM);   // [4][NPC]
+	uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + 4 * NPC);                                   // [0]: samples in, [1]: results in
+	if constexpr (CL) {
+		cg::cluster_group cluster = cg::this_cluster();
+		crank = cluster.block_rank();
+		if (threadIdx.x == 0) {
+			mbar_init(&mbar[0], 1);
+			mbar_init(&mbar[1], 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			mbar_arrive_expect_tx(&mbar[0], (unsigned) (CPB * (N / 2) * sizeof(double2)));   // every packed pair of this CTA's channels
+			mbar_arrive_expect_tx(&mbar[1], (unsigned) (4 * NPC * sizeof(double2)));         // this CTA's rows of all four channels
+		}
+		cluster.sync();   // mbarriers armed, every CTA running (nothing in flight yet: this fence is free)
+	}
+#else
 	double2 *rbuf[4] = { buf, buf, buf, buf };
 	if constexpr (CL) {
 		cg::cluster_group cluster = cg::this_cluster();
@@ -340,6 +413,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		for (int c = 0; c < 4; ++c) rbuf[c] = cluster.map_shared_rank(smem + (size_t) (c % CPB) * FftCfg<N>::STRIDE, c / CPB);
 		cluster.sync();   // a CTA's shared memory may only be touched once that CTA is known to be running
 	}
+#endif
 
 	if (active) {
 		double2 v[8];
@@ -352,10 +426,20 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 				const double *r0 = xr + 2L * n * a.xin_stride, *r1 = r0 + a.xin_stride;
 				const double2 a0 = *reinterpret_cast<const double2 *>(r0), a1 = *reinterpret_cast<const double2 *>(r0 + 2);
 				const double2 b0 = *reinterpret_cast<const double2 *>(r1), b1 = *reinterpret_cast<const double2 *>(r1 + 2);
+#if FIR_L0_ASYNC
+				// channel c of the four lives in CTA c / CPB, transform buffer c % CPB
+				const uint32_t off = (uint32_t) (spad(n) * sizeof(double2));
+				const uint32_t b_lo = smem_u32(smem) + off, b_hi = smem_u32(smem + (size_t) (CPB - 1) * FftCfg<N>::STRIDE) + off, mb = smem_u32(&mbar[0]);
+				st_async_f64x2(mapa_u32(b_lo, 0 / CPB), a0.x, b0.x, mapa_u32(mb, 0 / CPB));
+				st_async_f64x2(mapa_u32((CPB == 2) ? b_hi : b_lo, 1 / CPB), a0.y, b0.y, mapa_u32(mb, 1 / CPB));
+				st_async_f64x2(mapa_u32(b_lo, 2 / CPB), a1.x, b1.x, mapa_u32(mb, 2 / CPB));
+				st_async_f64x2(mapa_u32((CPB == 2) ? b_hi : b_lo, 3 / CPB), a1.y, b1.y, mapa_u32(mb, 3 / CPB));
+#else
 				rbuf[0][spad(n)] = make_double2(a0.x, b0.x);
 				rbuf[1][spad(n)] = make_double2(a0.y, b0.y);
 				rbuf[2][spad(n)] = make_double2(a1.x, b1.x);
 				rbuf[3][spad(n)] = make_double2(a1.y, b1.y);
+#endif
 			}
 		}
 		else if (a.xin) {
@@ -373,28 +457,34 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #pragma unroll
 			for (int i = 0; i < 8; ++i) v[i] = x[t + i * T];
 		}
-		// what the middle and the last phase will read from HBM: start it moving towards L2 now, so that it
-		// arrives while the first transform runs (the CTA's warps all sit in the same phase, nothing else hides it)
-		{
-			const double2 *Hc = a.H + (long) s * a.h_ch_stride;
-			prefetch_rows(Hc, (long) P * N * sizeof(double2), t, T);
-			const double2 *fc_ = a.fdl + (long) s * a.fdl_ch_stride;
-#pragma unroll
-			for (int p = 1; p < P; ++p) {
-				const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
-				prefetch_rows(fc_ + (long) sl * N, (long) N * sizeof(double2), t, T);
-			}
-			prefetch_rows(a.carry + (long) s * N, (long) N * sizeof(double), t, T);
-			if (a.init) prefetch_rows(a.init + (long) s * N, (long) N * sizeof(double2), t, T);
-		}
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			if (!CL) buf[spad(t + i * T)] = v[i];
 			buf[spad(t + i * T + N / 2)] = make_double2(0.0, 0.0);
 		}
 	}
+#if FIR_L0_ASYNC
+	if constexpr (CL) mbar_wait_cluster(&mbar[0], 0);   // the samples of this CTA's channels, from every CTA of the cluster
+	__syncthreads();
+#else
 	if constexpr (CL) cg::this_cluster().sync();
 	else __syncthreads();
+#endif
+	if (active) {
+		// what the middle and the last phase will read from HBM: start it moving towards L2 now, so that it
+		// arrives while the first transform runs (the CTA's warps all sit in the same phase, nothing else hides it).
+		// After the barrier: its release fence would wait for these requests too.
+		const double2 *Hc = a.H + (long) s * a.h_ch_stride;
+		prefetch_rows(Hc, (long) P * N * sizeof(double2), t, T);
+		const double2 *fc_ = a.fdl + (long) s * a.fdl_ch_stride;
+#pragma unroll
+		for (int p = 1; p < P; ++p) {
+			const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
+			prefetch_rows(fc_ + (long) sl * N, (long) N * sizeof(double2), t, T);
+		}
+		prefetch_rows(a.carry + (long) s * N, (long) N * sizeof(double), t, T);
+		if (a.init) prefetch_rows(a.init + (long) s * N, (long) N * sizeof(double2), t, T);
+	}
 	fft_forward_smem<N>(buf, a.ptw, t);
 	if (active) {
 		double2 *fdl = a.fdl + (long) s * a.fdl_ch_stride;
@@ -483,20 +573,48 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 			const int n = t + i * T;
 			const double2 lo = buf[spad(n)], hi = buf[spad(n + N / 2)];
 			const double2 y = make_double2(fma(lo.x, scale, c[i].x), fma(-lo.y, scale, c[i].y));
-			if (CL) buf[spad(n)] = y;   // this thread is the only one that touches entry n after the last pass
+			if (CL) {
+#if FIR_L0_ASYNC
+				// to the CTA that writes rows n: its staging area, row of this channel; the bytes count on its mbarrier
+				constexpr int IPW = NPC / T;                 // this thread's entries i that share a writer
+				const int wr = i / IPW;                      // n / NPC (t < T)
+				const int cc = (int) crank * CPB + g;        // this channel within the cluster's four
+				const uint32_t dst = smem_u32(stage + (size_t) cc * NPC + (n - wr * NPC));
+				st_async_f64x2(mapa_u32(dst, wr), y.x, y.y, mapa_u32(smem_u32(&mbar[1]), wr));
+				carry[n] = make_double2(hi.x * scale, -hi.y * scale);
+#else
+				buf[spad(n)] = y;   // this thread is the only one that touches entry n after the last pass
+#endif
+			}
 			else if (yc) {
 				yc[2L * n * a.yout_stride] = y.x;
 				yc[(2L * n + 1) * a.yout_stride] = y.y;
 			}
 			else out[n] = y;
-			carry[n] = make_double2(hi.x * scale, -hi.y * scale);
+			// (cluster form with fenced barriers: the new carry is stored after the barrier below -- its release fence
+			// would wait for these stores; the second half of the buffer, where it comes from, is nobody else's)
+			if (!CL) carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 		}
 	}
 	if constexpr (CL) {
-		cg::cluster_group cluster = cg::this_cluster();
-		cluster.sync();   // all four channels' results are in their owners' buffers
 		const int s0 = ((int) blockIdx.x - (int) crank) * CPB;
 		double *yr = a.yout + (a.yout_map ? a.yout_map[s0] : s0);
+#if FIR_L0_ASYNC
+		mbar_wait_cluster(&mbar[1], 0);   // this CTA's rows of all four channels have landed in `stage`
+#pragma unroll
+		for (int i = 0; i < NPC / THREADS; ++i) {
+			const int nl = (int) threadIdx.x + i * THREADS, n = (int) crank * NPC + nl;
+			const double2 y0 = stage[nl], y1 = stage[NPC + nl], y2 = stage[2 * NPC + nl], y3 = stage[3 * NPC + nl];
+			double *r0 = yr + 2L * n * a.yout_stride, *r1 = r0 + a.yout_stride;
+			*reinterpret_cast<double2 *>(r0) = make_double2(y0.x, y1.x);
+			*reinterpret_cast<double2 *>(r0 + 2) = make_double2(y2.x, y3.x);
+			*reinterpret_cast<double2 *>(r1) = make_double2(y0.y, y1.y);
+			*reinterpret_cast<double2 *>(r1 + 2) = make_double2(y2.y, y3.y);
+		}
+		cluster_barrier_relaxed();   // nobody leaves while a neighbour may still be sending to it (execution only)
+#else
+		cg::cluster_group cluster = cg::this_cluster();
+		cluster.sync();   // all four channels' results are in their owners' buffers
 #pragma unroll
 		for (int i = 0; i < NPC / THREADS; ++i) {
 			const int n = (int) crank * NPC + (int) threadIdx.x + i * THREADS;
@@ -507,7 +625,18 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 			*reinterpret_cast<double2 *>(r1) = make_double2(y0.y, y1.y);
 			*reinterpret_cast<double2 *>(r1 + 2) = make_double2(y2.y, y3.y);
 		}
-		cluster.sync();   // nobody leaves while its buffer may still be read
+		{
+			const double scale = 1.0 / N;
+			double2 *carry = reinterpret_cast<double2 *>(a.carry + (long) s * N);
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				const int n = t + i * T;
+				const double2 hi = buf[spad(n + N / 2)];
+				carry[n] = make_double2(hi.x * scale, -hi.y * scale);
+			}
+		}
+		cluster_barrier_relaxed();   // nobody leaves while its buffer may still be read (execution only: nothing to publish)
+#endif
 	}
 }
 
@@ -901,10 +1030,10 @@ __global__ void k_delay_write(const double *y, long y_stride, double *ring, int 
 // (DSP_B200_FIR_L0_SMEM_KB: a way to cap its CTAs per SM, so that the streaming kernels of the other streams find
 // registers next to it)
 template <int N>
-static size_t level0_smem()
+static size_t level0_smem(bool cluster_form = false)
 {
 	static const long want = getenv("DSP_B200_FIR_L0_SMEM_KB") ? atol(getenv("DSP_B200_FIR_L0_SMEM_KB")) * 1024 : 0;
-	size_t n = FftCfg<N>::SMEM;
+	size_t n = cluster_form ? L0ClCfg<N>::SMEM : FftCfg<N>::SMEM;
 	if (N >= 2048 && want > (long) n) n = (size_t) ((want > 227 * 1024) ? 227 * 1024 : want);
 	return n;
 }
@@ -921,8 +1050,8 @@ static int configure_n()
 		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
 		CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
 		if constexpr (FftCfg<N>::CPB <= 2) {
-			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
-			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>()), return -1);
+			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>(true)), return -1);
+			CUDA_TRY(cudaFuncSetAttribute((k_fir_level0<N, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) level0_smem<N>(true)), return -1);
 		}
 		configured[dev & 63].store(1);
 	}
@@ -959,7 +1088,7 @@ static int launch_level0_n(const L0Args &a, cudaStream_t st)
 		if (a.cluster_io) {
 			constexpr int CPB = FftCfg<N>::CPB;
 			cudaLaunchConfig_t cfg = {};
-			cfg.gridDim = dim3(a.n_ch / CPB); cfg.blockDim = dim3(FftCfg<N>::THREADS); cfg.dynamicSmemBytes = level0_smem<N>(); cfg.stream = st;
+			cfg.gridDim = dim3(a.n_ch / CPB); cfg.blockDim = dim3(FftCfg<N>::THREADS); cfg.dynamicSmemBytes = level0_smem<N>(true); cfg.stream = st;
 			cudaLaunchAttribute attr;
 			attr.id = cudaLaunchAttributeClusterDimension;
 			attr.val.clusterDim.x = 4 / CPB; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
