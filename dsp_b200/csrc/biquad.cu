@@ -33,7 +33,7 @@ namespace dspb200 {
 
 constexpr int BQ_L = 16;           // frames per lane
 constexpr int BQ_MAX_STAGES = 16;  // stages fused into one operator
-constexpr int BQ_NPOW = 8;         // A^(L 2^r), r = 0..7: chunks within a warp (r < LOGW), warps within a tile (LOGW <= r)
+constexpr int BQ_NPOW = 6;         // A^(L 2^r), r = 0..5
 // per channel and stage: 5 coefficients (+1 pad), BQ_NPOW 2x2 matrices, and G[i] = A^(L-1-i) B (2 x L), contiguous;
 // every piece starts on a 16-byte boundary so that the kernel reads the table with 128-bit shared loads
 constexpr int BQ_OFF_P = 6, BQ_OFF_G = BQ_OFF_P + 4 * BQ_NPOW;
@@ -62,7 +62,6 @@ struct BqCfg {
 	static constexpr int CPW = 32 / CH;                         // chunks per warp
 	static constexpr int LOGW = (CH == 1) ? 5 : (CH == 2) ? 4 : 3;
 	static constexpr int WARPS = SPLIT ? 8 : (CH == 1) ? 8 : 16;
-	static constexpr int LOGWARPS = (WARPS == 8) ? 3 : 4;
 	static constexpr int THREADS = 32 * WARPS;
 	static constexpr long TILE = (long) BQ_L * CPW * WARPS;     // frames per tile
 };
@@ -160,36 +159,9 @@ __global__ void __launch_bounds__(BqCfg<CH, SPLIT>::THREADS, SPLIT ? 2 : 1) k_bq
 			__syncthreads();
 			// (3) carry into this warp, then into this lane
 			double2 cin = carry[st][ch];
-			if constexpr (CH == 4) {
-				for (int k = 0; k < w; ++k) {
-					const double2 u = m2_apply(P[LOGW], cin);
-					cin = make_double2(u.x + tot[k][ch].x, u.y + tot[k][ch].y);
-				}
-			}
-			else {
-				// the same scan once more, over the warps' totals (a warp spans A^(L 2^LOGW)): lane (k, ch) takes warp k's
-				// total, warp 0's also carries the tile's incoming state; the inclusive result of warp w-1 is what enters
-				// warp w.  Every warp does this redundantly -- log2(WARPS) rounds instead of up to WARPS-1 serial steps.
-				const int kk = lane / CH;
-				double2 e = (kk < Cfg::WARPS) ? tot[kk][ch] : make_double2(0.0, 0.0);
-				if (kk == 0) {
-					const double2 u = m2_apply(P[LOGW], cin);
-					e.x += u.x;
-					e.y += u.y;
-				}
-#pragma unroll
-				for (int r = 0; r < Cfg::LOGWARPS; ++r) {
-					const double vx = __shfl_up_sync(0xffffffffu, e.x, CH << r), vy = __shfl_up_sync(0xffffffffu, e.y, CH << r);
-					if (kk >= (1 << r)) {
-						const double2 lo = t[BQ_OFF_P / 2 + 2 * (LOGW + r)], hi = t[BQ_OFF_P / 2 + 2 * (LOGW + r) + 1];   // A^(L 2^(LOGW+r))
-						const double2 u = m2_apply(M2{ lo.x, lo.y, hi.x, hi.y }, make_double2(vx, vy));
-						e.x += u.x;
-						e.y += u.y;
-					}
-				}
-				const int src = (w > 0) ? (w - 1) * CH + ch : 0;
-				const double sx = __shfl_sync(0xffffffffu, e.x, src), sy = __shfl_sync(0xffffffffu, e.y, src);
-				if (w > 0) cin = make_double2(sx, sy);
+			for (int k = 0; k < w; ++k) {
+				const double2 u = m2_apply(P[LOGW], cin);
+				cin = make_double2(u.x + tot[k][ch].x, u.y + tot[k][ch].y);
 			}
 #pragma unroll
 			for (int r = 0; r < LOGW; ++r)

@@ -303,12 +303,16 @@ __device__ __forceinline__ void prefetch_rows(const void *p, long bytes, int t, 
 	for (long off = (long) t * 128; off < bytes; off += (long) T * 128) prefetch_l2(c + off);
 }
 
-// FIR_L0_ASYNC (default): the cluster form of the fused kernel moves its samples between the CTAs of a cluster with
-// st.async -- remote shared-memory stores that complete bytes on the RECEIVER's mbarrier -- instead of plain
-// distributed-shared-memory stores fenced by cluster.sync().  The releasing cluster barrier compiles to MEMBAR.ALL.GPU
-// (+ ERRBAR): every thread waits for all its global stores and prefetches in flight, four times per block; a third of
-// the kernel's stall samples were that wait (profiles/r02_prof_fir_step_*).  With st.async nobody fences: a CTA
-// waits on its own mbarrier until the bytes addressed to it have landed.
+// FIR_L0_ASYNC: the cluster form of the fused kernel exchanges its samples between the CTAs of a cluster with bulk
+// copies shared memory -> a neighbour's shared memory that complete bytes on the RECEIVER's mbarrier
+// (cp.async.bulk.shared::cluster.shared::cta), instead of plain distributed-shared-memory stores fenced by
+// cluster.sync().  The releasing cluster barrier compiles to MEMBAR.ALL.GPU (+ ERRBAR): every thread waits for all its
+// global stores and prefetches in flight, four times per block; a third of the kernel's stall samples were that wait
+// (profiles/r02_prof_fir_step_*).  Here nobody fences: a CTA de-interleaves its rows into a staging area, one thread
+// sends each channel's chunk (8.5 KB, already in the padded layout of the transform buffer) to its owner, and a CTA
+// waits on its own mbarrier until the bytes addressed to it have landed.  (Per-element st.async -- 16 bytes and one
+// transaction-count update on the receiver's mbarrier each -- measured slower than the fenced form: 52 against
+// 43.5 us.)  0 selects the fenced form.
 #ifndef FIR_L0_ASYNC
 #define FIR_L0_ASYNC 1
 #endif
@@ -318,8 +322,10 @@ struct L0ClCfg {
 	static constexpr int CPB = FftCfg<N>::CPB;
 	static constexpr int NCL = (CPB <= 2) ? 4 / CPB : 1;   // CTAs per cluster
 	static constexpr int NPC = N / 2 / NCL;                // packed frame pairs a CTA moves for all four channels
-	// after the transform buffers: result staging [4 channels][NPC] and two mbarriers (samples in, results in)
-	static constexpr size_t STAGE_BYTES = (size_t) 4 * NPC * sizeof(double2);
+	static constexpr int CHUNK = NPC + NPC / 16;           // the same, in the padded layout of the transform buffers (spad())
+	// after the transform buffers: staging [4 channels][CHUNK] (this CTA's rows of all four channels: on the way in
+	// what it read, on the way out what it is about to write) and two mbarriers (samples in, results in)
+	static constexpr size_t STAGE_BYTES = (size_t) 4 * CHUNK * sizeof(double2);
 	static constexpr size_t SMEM = FIR_L0_ASYNC ? FftCfg<N>::SMEM + STAGE_BYTES + 16 : FftCfg<N>::SMEM;
 };
 
@@ -330,14 +336,22 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank)
 	return r;
 }
 
-// 16 bytes into the shared memory of a CTA of the cluster; the bytes count on that CTA's mbarrier when they have landed
-__device__ __forceinline__ void st_async_f64x2(uint32_t dst, double x, double y, uint32_t mbar)
+// `bytes` (a multiple of 16) from this CTA's shared memory into the shared memory of a CTA of the cluster; they count on
+// that CTA's mbarrier when they have landed.  Issued by one thread.
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, unsigned bytes, uint32_t mbar_cluster)
 {
-	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst), "d"(x), "d"(y), "r"(mbar)
+	asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(src_cta),
+	             "r"(bytes), "r"(mbar_cluster)
 	             : "memory");
 }
 
-// wait for a phase completed by other CTAs' st.async (acquire at cluster scope); traps instead of hanging
+// generic-proxy writes to shared memory before, async-proxy (bulk copy) reads of them after
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// wait for a phase completed by other CTAs' bulk copies (acquire at cluster scope); traps instead of hanging
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, unsigned parity)
 {
 	unsigned spins = 0;
@@ -390,8 +404,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 	namespace cg = cooperative_groups;
 	unsigned crank = 0;
 #if FIR_L0_ASYNC
-	double2 *stage = reinterpret_cast<double2 *>(reinterpret_cast<char *>(smem) + FftCfg<N>::SMEM);   // [4][NPC]
-	uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + 4 * NPC);                                   // [0]: samples in, [1]: results in
+	constexpr int CHUNK = NPC + NPC / 16;
+	constexpr unsigned CHUNK_BYTES = CHUNK * sizeof(double2);
+	double2 *stage = reinterpret_cast<double2 *>(reinterpret_cast<char *>(smem) + FftCfg<N>::SMEM);   // [4][CHUNK]
+	uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + 4 * CHUNK);                                 // [0]: samples in, [1]: results in
 	if constexpr (CL) {
 		cg::cluster_group cluster = cg::this_cluster();
 		crank = cluster.block_rank();
@@ -399,8 +415,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 			mbar_init(&mbar[0], 1);
 			mbar_init(&mbar[1], 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-			mbar_arrive_expect_tx(&mbar[0], (unsigned) (CPB * (N / 2) * sizeof(double2)));   // every packed pair of this CTA's channels
-			mbar_arrive_expect_tx(&mbar[1], (unsigned) (4 * NPC * sizeof(double2)));         // this CTA's rows of all four channels
+			mbar_arrive_expect_tx(&mbar[0], CPB * NCL * CHUNK_BYTES);   // the first half of this CTA's transform buffers
+			mbar_arrive_expect_tx(&mbar[1], 4 * CHUNK_BYTES);           // this CTA's rows of all four channels
 		}
 		cluster.sync();   // mbarriers armed, every CTA running (nothing in flight yet: this fence is free)
 	}
@@ -427,13 +443,11 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 				const double2 a0 = *reinterpret_cast<const double2 *>(r0), a1 = *reinterpret_cast<const double2 *>(r0 + 2);
 				const double2 b0 = *reinterpret_cast<const double2 *>(r1), b1 = *reinterpret_cast<const double2 *>(r1 + 2);
 #if FIR_L0_ASYNC
-				// channel c of the four lives in CTA c / CPB, transform buffer c % CPB
-				const uint32_t off = (uint32_t) (spad(n) * sizeof(double2));
-				const uint32_t b_lo = smem_u32(smem) + off, b_hi = smem_u32(smem + (size_t) (CPB - 1) * FftCfg<N>::STRIDE) + off, mb = smem_u32(&mbar[0]);
-				st_async_f64x2(mapa_u32(b_lo, 0 / CPB), a0.x, b0.x, mapa_u32(mb, 0 / CPB));
-				st_async_f64x2(mapa_u32((CPB == 2) ? b_hi : b_lo, 1 / CPB), a0.y, b0.y, mapa_u32(mb, 1 / CPB));
-				st_async_f64x2(mapa_u32(b_lo, 2 / CPB), a1.x, b1.x, mapa_u32(mb, 2 / CPB));
-				st_async_f64x2(mapa_u32((CPB == 2) ? b_hi : b_lo, 3 / CPB), a1.y, b1.y, mapa_u32(mb, 3 / CPB));
+				const int nl = spad((int) threadIdx.x + i * THREADS);   // within this CTA's rows; its first row is a multiple of 16
+				stage[nl] = make_double2(a0.x, b0.x);
+				stage[CHUNK + nl] = make_double2(a0.y, b0.y);
+				stage[2 * CHUNK + nl] = make_double2(a1.x, b1.x);
+				stage[3 * CHUNK + nl] = make_double2(a1.y, b1.y);
 #else
 				rbuf[0][spad(n)] = make_double2(a0.x, b0.x);
 				rbuf[1][spad(n)] = make_double2(a0.y, b0.y);
@@ -464,8 +478,21 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		}
 	}
 #if FIR_L0_ASYNC
-	if constexpr (CL) mbar_wait_cluster(&mbar[0], 0);   // the samples of this CTA's channels, from every CTA of the cluster
-	__syncthreads();
+	if constexpr (CL) {
+		fence_proxy_async_smem();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			// channel c of the four lives in CTA c / CPB, transform buffer c % CPB; this CTA's rows start at crank * NPC
+			const uint32_t mb = smem_u32(&mbar[0]);
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const uint32_t dst = smem_u32(smem + (size_t) (c % CPB) * FftCfg<N>::STRIDE + spad((int) crank * NPC));
+				bulk_s2c(mapa_u32(dst, c / CPB), smem_u32(stage + (size_t) c * CHUNK), CHUNK_BYTES, mapa_u32(mb, c / CPB));
+			}
+		}
+		mbar_wait_cluster(&mbar[0], 0);   // the samples of this CTA's channels, from every CTA of the cluster
+	}
+	else __syncthreads();
 #else
 	if constexpr (CL) cg::this_cluster().sync();
 	else __syncthreads();
@@ -575,12 +602,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 			const double2 y = make_double2(fma(lo.x, scale, c[i].x), fma(-lo.y, scale, c[i].y));
 			if (CL) {
 #if FIR_L0_ASYNC
-				// to the CTA that writes rows n: its staging area, row of this channel; the bytes count on its mbarrier
-				constexpr int IPW = NPC / T;                 // this thread's entries i that share a writer
-				const int wr = i / IPW;                      // n / NPC (t < T)
-				const int cc = (int) crank * CPB + g;        // this channel within the cluster's four
-				const uint32_t dst = smem_u32(stage + (size_t) cc * NPC + (n - wr * NPC));
-				st_async_f64x2(mapa_u32(dst, wr), y.x, y.y, mapa_u32(smem_u32(&mbar[1]), wr));
+				buf[spad(n)] = y;   // this thread is the only one that touches entry n after the last pass
 				carry[n] = make_double2(hi.x * scale, -hi.y * scale);
 #else
 				buf[spad(n)] = y;   // this thread is the only one that touches entry n after the last pass
@@ -600,18 +622,33 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		const int s0 = ((int) blockIdx.x - (int) crank) * CPB;
 		double *yr = a.yout + (a.yout_map ? a.yout_map[s0] : s0);
 #if FIR_L0_ASYNC
+		fence_proxy_async_smem();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			// rows [wr * NPC, (wr + 1) * NPC) of every channel of this CTA go to CTA wr, which writes them
+			const uint32_t mb = smem_u32(&mbar[1]);
+#pragma unroll
+			for (int wr = 0; wr < NCL; ++wr) {
+#pragma unroll
+				for (int gg = 0; gg < CPB; ++gg) {
+					const int cc = (int) crank * CPB + gg;   // this channel within the cluster's four
+					bulk_s2c(mapa_u32(smem_u32(stage + (size_t) cc * CHUNK), wr), smem_u32(smem + (size_t) gg * FftCfg<N>::STRIDE + spad(wr * NPC)),
+					         CHUNK_BYTES, mapa_u32(mb, wr));
+				}
+			}
+		}
 		mbar_wait_cluster(&mbar[1], 0);   // this CTA's rows of all four channels have landed in `stage`
 #pragma unroll
 		for (int i = 0; i < NPC / THREADS; ++i) {
-			const int nl = (int) threadIdx.x + i * THREADS, n = (int) crank * NPC + nl;
-			const double2 y0 = stage[nl], y1 = stage[NPC + nl], y2 = stage[2 * NPC + nl], y3 = stage[3 * NPC + nl];
+			const int n = (int) crank * NPC + (int) threadIdx.x + i * THREADS, nl = spad((int) threadIdx.x + i * THREADS);
+			const double2 y0 = stage[nl], y1 = stage[CHUNK + nl], y2 = stage[2 * CHUNK + nl], y3 = stage[3 * CHUNK + nl];
 			double *r0 = yr + 2L * n * a.yout_stride, *r1 = r0 + a.yout_stride;
 			*reinterpret_cast<double2 *>(r0) = make_double2(y0.x, y1.x);
 			*reinterpret_cast<double2 *>(r0 + 2) = make_double2(y2.x, y3.x);
 			*reinterpret_cast<double2 *>(r1) = make_double2(y0.y, y1.y);
 			*reinterpret_cast<double2 *>(r1 + 2) = make_double2(y2.y, y3.y);
 		}
-		cluster_barrier_relaxed();   // nobody leaves while a neighbour may still be sending to it (execution only)
+		cluster_barrier_relaxed();   // nobody leaves before the copies out of its shared memory are complete (execution only)
 #else
 		cg::cluster_group cluster = cg::this_cluster();
 		cluster.sync();   // all four channels' results are in their owners' buffers
@@ -1281,6 +1318,11 @@ struct FirOp : Op {
 	int ev_bs_n = 0;
 	cudaEvent_t ev_bs_last = nullptr;
 	cudaEvent_t ev_join[2] = { nullptr, nullptr };
+	// single-level tail plans: the fused kernel of every block goes to a stream of the highest priority (the caller's
+	// stream hands over and takes back with two events): its CTAs are placed before the queued CTAs of the
+	// look-ahead MACs, which share the lowest priority with a caller's default stream otherwise
+	cudaStream_t hot = nullptr;
+	cudaEvent_t ev_hot_in = nullptr, ev_hot_out = nullptr;
 	bool urgent_pending = false;
 	long ltmp_cap = 0;
 	// bulk form (single-level plans): up to nb_max whole blocks of one call are transformed, multiplied and
@@ -1320,6 +1362,14 @@ struct FirOp : Op {
 			cudaStreamDestroy(side2);
 			side2 = nullptr;
 		}
+		if (hot) {
+			cudaStreamSynchronize(hot);
+			cudaStreamDestroy(hot);
+			hot = nullptr;
+		}
+		if (ev_hot_in) cudaEventDestroy(ev_hot_in);
+		if (ev_hot_out) cudaEventDestroy(ev_hot_out);
+		ev_hot_in = ev_hot_out = nullptr;
 		for (cudaEvent_t &e : ev_batch) { if (e) cudaEventDestroy(e); e = nullptr; }
 		for (cudaEvent_t &e : ev_bs) { if (e) cudaEventDestroy(e); e = nullptr; }
 		ev_bs_last = nullptr; ev_bs_n = 0;
@@ -1428,6 +1478,14 @@ struct FirOp : Op {
 				if (!use_pipe) {
 					d_Y_side = dev_alloc<double2>((size_t) pf * n_sel * L.B);
 					if (!d_Y_side) return -1;
+				}
+				const char *he = getenv("DSP_B200_FIR_HOT");
+				if (!use_pipe && l == 0 && direct_io && !(he && he[0] == '0')) {
+					int lo = 0, hi = 0;
+					cudaDeviceGetStreamPriorityRange(&lo, &hi);
+					CUDA_TRY(cudaStreamCreateWithPriority(&hot, cudaStreamNonBlocking, hi), return -1);
+					CUDA_TRY(cudaEventCreateWithFlags(&ev_hot_in, cudaEventDisableTiming), return -1);
+					CUDA_TRY(cudaEventCreateWithFlags(&ev_hot_out, cudaEventDisableTiming), return -1);
 				}
 				const char *nb = getenv("DSP_B200_FIR_NO_BATCH");
 				int tb = FIR_T_BATCH;
@@ -1979,12 +2037,23 @@ struct FirOp : Op {
 					f.H = L0.H; f.h_ch_stride = (fc == 1) ? 0 : (long) L0.P * B0;
 					f.P = (L0.P < 2) ? L0.P : 2; f.slot = (int) (L0.blk % L0.R);
 					f.out = d_ytmp; f.out_ch_stride = B0; f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
+					cudaStream_t ls = st;
+					const bool use_hot = hot && direct && tail_pf == 2 && !g_fir_serialize.load(std::memory_order_relaxed);
+					if (use_hot) {
+						CUDA_TRY(cudaEventRecord(ev_hot_in, st), return -1);
+						CUDA_TRY(cudaStreamWaitEvent(hot, ev_hot_in, 0), return -1);
+						ls = hot;
+					}
 					if (tail_pf == 2 && L0.blk >= 2) {
 						// Y of this block was launched two blocks ago (advance_tail0)
-						CUDA_TRY(cudaStreamWaitEvent(st, ev_tail[L0.blk & 1], 0), return -1);
+						CUDA_TRY(cudaStreamWaitEvent(ls, ev_tail[L0.blk & 1], 0), return -1);
 						f.init = d_Y_side + (size_t) (L0.blk & 1) * n_sel * B0;
 					}
-					if (launch_level0(B0, f, st)) return -1;
+					if (launch_level0(B0, f, ls)) return -1;
+					if (use_hot) {
+						CUDA_TRY(cudaEventRecord(ev_hot_out, hot), return -1);
+						CUDA_TRY(cudaStreamWaitEvent(st, ev_hot_out, 0), return -1);
+					}
 					++L0.blk;
 				}
 				else if (level_block(L0, d_ytmp, B0, INV_OUT | INV_UPDATE_CARRY, st)) return -1;
