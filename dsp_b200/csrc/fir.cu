@@ -323,10 +323,12 @@ struct L0ClCfg {
 	static constexpr int NCL = (CPB <= 2) ? 4 / CPB : 1;   // CTAs per cluster
 	static constexpr int NPC = N / 2 / NCL;                // packed frame pairs a CTA moves for all four channels
 	static constexpr int CHUNK = NPC + NPC / 16;           // the same, in the padded layout of the transform buffers (spad())
-	// after the transform buffers: staging [4 channels][CHUNK] (this CTA's rows of all four channels: on the way in
-	// what it read, on the way out what it is about to write) and two mbarriers (samples in, results in)
-	static constexpr size_t STAGE_BYTES = (size_t) 4 * CHUNK * sizeof(double2);
-	static constexpr size_t SMEM = FIR_L0_ASYNC ? FftCfg<N>::SMEM + STAGE_BYTES + 16 : FftCfg<N>::SMEM;
+	// Staging (this CTA's rows of all four channels: on the way in what it read, on the way out what it is about to
+	// write) = the SECOND halves of its transform buffers, which hold exactly 4 chunks: they are zeros on the way in
+	// (filled after the exchange) and the new carry on the way out (stored before the exchange).  A separate 34 KB
+	// staging area cost more than the fences it saved: the kernel runs 2 CTAs per SM and lives on what is left of
+	// the L1 (measured: 43.5 us at 69.6 KB per CTA, 45.8 at 86, 53.6 at 103).  After the buffers: two mbarriers.
+	static constexpr size_t SMEM = FIR_L0_ASYNC ? FftCfg<N>::SMEM + 16 : FftCfg<N>::SMEM;
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank)
@@ -406,8 +408,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #if FIR_L0_ASYNC
 	constexpr int CHUNK = NPC + NPC / 16;
 	constexpr unsigned CHUNK_BYTES = CHUNK * sizeof(double2);
-	double2 *stage = reinterpret_cast<double2 *>(reinterpret_cast<char *>(smem) + FftCfg<N>::SMEM);   // [4][CHUNK]
-	uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + 4 * CHUNK);                                 // [0]: samples in, [1]: results in
+	// staging chunk c (channel c of the cluster's four): the second half of a transform buffer holds NCL chunks
+	auto stage = [&](int c) -> double2 * { return smem + (size_t) (c / NCL) * FftCfg<N>::STRIDE + spad(N / 2) + (size_t) (c % NCL) * CHUNK; };
+	uint64_t *mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(smem) + FftCfg<N>::SMEM);   // [0]: samples in, [1]: results in
 	if constexpr (CL) {
 		cg::cluster_group cluster = cg::this_cluster();
 		crank = cluster.block_rank();
@@ -444,10 +447,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 				const double2 b0 = *reinterpret_cast<const double2 *>(r1), b1 = *reinterpret_cast<const double2 *>(r1 + 2);
 #if FIR_L0_ASYNC
 				const int nl = spad((int) threadIdx.x + i * THREADS);   // within this CTA's rows; its first row is a multiple of 16
-				stage[nl] = make_double2(a0.x, b0.x);
-				stage[CHUNK + nl] = make_double2(a0.y, b0.y);
-				stage[2 * CHUNK + nl] = make_double2(a1.x, b1.x);
-				stage[3 * CHUNK + nl] = make_double2(a1.y, b1.y);
+				stage(0)[nl] = make_double2(a0.x, b0.x);
+				stage(1)[nl] = make_double2(a0.y, b0.y);
+				stage(2)[nl] = make_double2(a1.x, b1.x);
+				stage(3)[nl] = make_double2(a1.y, b1.y);
 #else
 				rbuf[0][spad(n)] = make_double2(a0.x, b0.x);
 				rbuf[1][spad(n)] = make_double2(a0.y, b0.y);
@@ -471,10 +474,12 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #pragma unroll
 			for (int i = 0; i < 8; ++i) v[i] = x[t + i * T];
 		}
+		if constexpr (!(CL && FIR_L0_ASYNC)) {
 #pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			if (!CL) buf[spad(t + i * T)] = v[i];
-			buf[spad(t + i * T + N / 2)] = make_double2(0.0, 0.0);
+			for (int i = 0; i < 8; ++i) {
+				if (!CL) buf[spad(t + i * T)] = v[i];
+				buf[spad(t + i * T + N / 2)] = make_double2(0.0, 0.0);
+			}
 		}
 	}
 #if FIR_L0_ASYNC
@@ -487,10 +492,15 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #pragma unroll
 			for (int c = 0; c < 4; ++c) {
 				const uint32_t dst = smem_u32(smem + (size_t) (c % CPB) * FftCfg<N>::STRIDE + spad((int) crank * NPC));
-				bulk_s2c(mapa_u32(dst, c / CPB), smem_u32(stage + (size_t) c * CHUNK), CHUNK_BYTES, mapa_u32(mb, c / CPB));
+				bulk_s2c(mapa_u32(dst, c / CPB), smem_u32(stage(c)), CHUNK_BYTES, mapa_u32(mb, c / CPB));
 			}
 		}
 		mbar_wait_cluster(&mbar[0], 0);   // the samples of this CTA's channels, from every CTA of the cluster
+		// every CTA has everything <=> every copy out of a staging area is complete: the second halves become zeros
+		cluster_barrier_relaxed();
+#pragma unroll
+		for (int i = 0; i < 8; ++i) buf[spad(t + i * T + N / 2)] = make_double2(0.0, 0.0);
+		__syncthreads();
 	}
 	else __syncthreads();
 #else
@@ -518,6 +528,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		const double2 *H = a.H + (long) s * a.h_ch_stride;
 		double2 *X = fdl + (long) a.slot * N;
 		const double2 *init = a.init ? a.init + (long) s * N : nullptr;
+		const bool per_ch_h = a.h_ch_stride != 0;
 		double2 w[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) w[i] = __ldg(&a.tw[t + i * T]);
@@ -550,8 +561,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 			const int n = (k == 0) ? N / 2 : N - k;
 			double2 Sk, Sn;
 			{
+				// rows that are read once go past the L1 (__ldcg): the kernel lives on what the two resident CTAs' buffers
+				// leave of it -- twiddle tables, and a shared filter
 				const double2 xk = buf[spad(k)], xn = buf[spad(n)];
-				const double2 hk = H[k], hn = H[n];
+				const double2 hk = per_ch_h ? __ldcg(&H[k]) : H[k], hn = per_ch_h ? __ldcg(&H[n]) : H[n];
 				if (k == 0) Sk = make_double2(xk.x * hk.x, xk.y * hk.y);   // packed bin: two real products
 				else Sk = cmul(xk, hk);
 				Sn = cmul(xn, hn);
@@ -559,8 +572,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #pragma unroll
 			for (int p = 1; p < P; ++p) {
 				const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
-				const double2 xk = fdl[(long) sl * N + k], xn = fdl[(long) sl * N + n];
-				const double2 hk = H[(long) p * N + k], hn = H[(long) p * N + n];
+				const double2 xk = __ldcg(&fdl[(long) sl * N + k]), xn = __ldcg(&fdl[(long) sl * N + n]);
+				const double2 hk = per_ch_h ? __ldcg(&H[(long) p * N + k]) : H[(long) p * N + k];
+				const double2 hn = per_ch_h ? __ldcg(&H[(long) p * N + n]) : H[(long) p * N + n];
 				if (k == 0) { Sk.x = fma(xk.x, hk.x, Sk.x); Sk.y = fma(xk.y, hk.y, Sk.y); }
 				else Sk = cmac(Sk, xk, hk);
 				Sn = cmac(Sn, xn, hn);
@@ -568,7 +582,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 			if (init) {
 				// what the other partitions of this level contribute (MAC kernels, a block period ahead):
 				// summed here, in the frequency domain, so that the level needs one inverse transform
-				const double2 yk = init[k], yn = init[n];
+				const double2 yk = __ldcg(&init[k]), yn = __ldcg(&init[n]);
 				Sk = cadd(Sk, yk);
 				Sn = cadd(Sn, yn);
 			}
@@ -594,7 +608,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		double *yc = a.yout ? a.yout + (a.yout_map ? a.yout_map[s] : s) : nullptr;
 		double2 c[8];
 #pragma unroll
-		for (int i = 0; i < 8; ++i) c[i] = carry[t + i * T];
+		for (int i = 0; i < 8; ++i) c[i] = __ldcg(&carry[t + i * T]);
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			const int n = t + i * T;
@@ -622,8 +636,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		const int s0 = ((int) blockIdx.x - (int) crank) * CPB;
 		double *yr = a.yout + (a.yout_map ? a.yout_map[s0] : s0);
 #if FIR_L0_ASYNC
+		// every thread of the cluster has read its second half (the carry stores above depend on those loads): the
+		// second halves are free to receive
 		fence_proxy_async_smem();
-		__syncthreads();
+		cluster_barrier_relaxed();
 		if (threadIdx.x == 0) {
 			// rows [wr * NPC, (wr + 1) * NPC) of every channel of this CTA go to CTA wr, which writes them
 			const uint32_t mb = smem_u32(&mbar[1]);
@@ -632,7 +648,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #pragma unroll
 				for (int gg = 0; gg < CPB; ++gg) {
 					const int cc = (int) crank * CPB + gg;   // this channel within the cluster's four
-					bulk_s2c(mapa_u32(smem_u32(stage + (size_t) cc * CHUNK), wr), smem_u32(smem + (size_t) gg * FftCfg<N>::STRIDE + spad(wr * NPC)),
+					bulk_s2c(mapa_u32(smem_u32(stage(cc)), wr), smem_u32(smem + (size_t) gg * FftCfg<N>::STRIDE + spad(wr * NPC)),
 					         CHUNK_BYTES, mapa_u32(mb, wr));
 				}
 			}
@@ -641,7 +657,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 #pragma unroll
 		for (int i = 0; i < NPC / THREADS; ++i) {
 			const int n = (int) crank * NPC + (int) threadIdx.x + i * THREADS, nl = spad((int) threadIdx.x + i * THREADS);
-			const double2 y0 = stage[nl], y1 = stage[CHUNK + nl], y2 = stage[2 * CHUNK + nl], y3 = stage[3 * CHUNK + nl];
+			const double2 y0 = stage(0)[nl], y1 = stage(1)[nl], y2 = stage(2)[nl], y3 = stage(3)[nl];
 			double *r0 = yr + 2L * n * a.yout_stride, *r1 = r0 + a.yout_stride;
 			*reinterpret_cast<double2 *>(r0) = make_double2(y0.x, y1.x);
 			*reinterpret_cast<double2 *>(r0 + 2) = make_double2(y2.x, y3.x);
