@@ -529,11 +529,12 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 		double2 *X = fdl + (long) a.slot * N;
 		const double2 *init = a.init ? a.init + (long) s * N : nullptr;
 		const bool per_ch_h = a.h_ch_stride != 0;
+		// (1) real split: X[k], X[N-k] to the FDL and, in place of Z, to shared memory.
+		//     Thread t owns the pairs k = t + i T; thread 0 also owns k = 0 (packed DC/Nyquist) and k = N/2.
+		//     (The twiddles are loaded again for the merge below: 32 registers that phase (2) has better use for.)
 		double2 w[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) w[i] = __ldg(&a.tw[t + i * T]);
-		// (1) real split: X[k], X[N-k] to the FDL and, in place of Z, to shared memory.
-		//     Thread t owns the pairs k = t + i T; thread 0 also owns k = 0 (packed DC/Nyquist) and k = N/2.
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			const int k = t + i * T;
@@ -553,51 +554,91 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS) __maxnreg__((N == 4096) ? 
 				buf[spad(k)] = xk; buf[spad(N - k)] = xn;
 			}
 		}
-		// (2) S = X_j H_0 + sum_{p>=1} X_{j-p} H_p for the owned bins (no global stores in this loop, so the
-		//     loads of all iterations can be in flight together), then the inverse merge into shared memory
+		// (2) S = X_j H_0 + sum_{p>=1} X_{j-p} H_p (+ Y_j) for the owned bins, one row (pair) at a time for all eight
+		//     bin pairs: 16 independent 16-byte loads in flight per pass instead of whatever fits next to the sums of
+		//     one bin pair -- the phase is a chain of memory round trips, nothing else.  The running sum is parked in
+		//     the buffer, in place of X_j (which is in the FDL by now).  Rows that are read once go past the L1
+		//     (__ldcg): the kernel lives on what the two resident CTAs' buffers leave of it (twiddle tables, a
+		//     shared filter).  Then the inverse merge.
+#define L0_K(i) (t + (i) * T)
+#define L0_N(i) ((L0_K(i) == 0) ? N / 2 : N - L0_K(i))
+		{
+			double2 hk[8], hn[8];
 #pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			const int k = t + i * T;
-			const int n = (k == 0) ? N / 2 : N - k;
-			double2 Sk, Sn;
-			{
-				// rows that are read once go past the L1 (__ldcg): the kernel lives on what the two resident CTAs' buffers
-				// leave of it -- twiddle tables, and a shared filter
+			for (int i = 0; i < 8; ++i) {
+				hk[i] = per_ch_h ? __ldcg(&H[L0_K(i)]) : H[L0_K(i)];
+				hn[i] = per_ch_h ? __ldcg(&H[L0_N(i)]) : H[L0_N(i)];
+			}
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				const int k = L0_K(i), n = L0_N(i);
 				const double2 xk = buf[spad(k)], xn = buf[spad(n)];
-				const double2 hk = per_ch_h ? __ldcg(&H[k]) : H[k], hn = per_ch_h ? __ldcg(&H[n]) : H[n];
-				if (k == 0) Sk = make_double2(xk.x * hk.x, xk.y * hk.y);   // packed bin: two real products
-				else Sk = cmul(xk, hk);
-				Sn = cmul(xn, hn);
-			}
-#pragma unroll
-			for (int p = 1; p < P; ++p) {
-				const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
-				const double2 xk = __ldcg(&fdl[(long) sl * N + k]), xn = __ldcg(&fdl[(long) sl * N + n]);
-				const double2 hk = per_ch_h ? __ldcg(&H[(long) p * N + k]) : H[(long) p * N + k];
-				const double2 hn = per_ch_h ? __ldcg(&H[(long) p * N + n]) : H[(long) p * N + n];
-				if (k == 0) { Sk.x = fma(xk.x, hk.x, Sk.x); Sk.y = fma(xk.y, hk.y, Sk.y); }
-				else Sk = cmac(Sk, xk, hk);
-				Sn = cmac(Sn, xn, hn);
-			}
-			if (init) {
-				// what the other partitions of this level contribute (MAC kernels, a block period ahead):
-				// summed here, in the frequency domain, so that the level needs one inverse transform
-				const double2 yk = __ldcg(&init[k]), yn = __ldcg(&init[n]);
-				Sk = cadd(Sk, yk);
-				Sn = cadd(Sn, yn);
-			}
-			if (k == 0) {
-				buf[0] = make_double2(0.5 * (Sk.x + Sk.y), -0.5 * (Sk.x - Sk.y));
-				buf[spad(N / 2)] = Sn;   // conj(Z[N/2]) = S[N/2]
-			}
-			else {
-				const double2 e = make_double2(0.5 * (Sk.x + Sn.x), 0.5 * (Sk.y - Sn.y));
-				const double2 d = make_double2(0.5 * (Sk.x - Sn.x), 0.5 * (Sk.y + Sn.y));
-				const double2 o = cmul(cconj(w[i]), d);
-				buf[spad(k)] = make_double2(e.x - o.y, -(e.y + o.x));
-				buf[spad(n)] = make_double2(e.x + o.y, -(o.x - e.y));
+				buf[spad(k)] = (k == 0) ? make_double2(xk.x * hk[i].x, xk.y * hk[i].y) : cmul(xk, hk[i]);   // packed bin: two real products
+				buf[spad(n)] = cmul(xn, hn[i]);
 			}
 		}
+#pragma unroll
+		for (int p = 1; p < P; ++p) {
+			const int sl = (a.slot - p < 0) ? a.slot - p + a.fdl_rows : a.slot - p;
+			const double2 *Xp = fdl + (long) sl * N, *Hp = H + (long) p * N;
+#pragma unroll
+			for (int half = 0; half < 8; half += 4) {
+				double2 xk[4], xn[4], hk[4], hn[4];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int k = L0_K(half + i), n = L0_N(half + i);
+					xk[i] = __ldcg(&Xp[k]);
+					xn[i] = __ldcg(&Xp[n]);
+					hk[i] = per_ch_h ? __ldcg(&Hp[k]) : Hp[k];
+					hn[i] = per_ch_h ? __ldcg(&Hp[n]) : Hp[n];
+				}
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int k = L0_K(half + i), n = L0_N(half + i);
+					double2 Sk = buf[spad(k)];
+					if (k == 0) { Sk.x = fma(xk[i].x, hk[i].x, Sk.x); Sk.y = fma(xk[i].y, hk[i].y, Sk.y); }
+					else Sk = cmac(Sk, xk[i], hk[i]);
+					buf[spad(k)] = Sk;
+					buf[spad(n)] = cmac(buf[spad(n)], xn[i], hn[i]);
+				}
+			}
+		}
+#pragma unroll
+		for (int half = 0; half < 8; half += 4) {
+			// what the other partitions of this level contribute (MAC kernels, a block period ahead): summed here, in
+			// the frequency domain, so that the level needs one inverse transform
+			double2 yk[4], yn[4], w2[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				w2[i] = __ldg(&a.tw[L0_K(half + i)]);
+				if (init) {
+					yk[i] = __ldcg(&init[L0_K(half + i)]);
+					yn[i] = __ldcg(&init[L0_N(half + i)]);
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int k = L0_K(half + i), n = L0_N(half + i);
+				double2 Sk = buf[spad(k)], Sn = buf[spad(n)];
+				if (init) {
+					Sk = cadd(Sk, yk[i]);
+					Sn = cadd(Sn, yn[i]);
+				}
+				if (k == 0) {
+					buf[0] = make_double2(0.5 * (Sk.x + Sk.y), -0.5 * (Sk.x - Sk.y));
+					buf[spad(N / 2)] = Sn;   // conj(Z[N/2]) = S[N/2]
+				}
+				else {
+					const double2 e = make_double2(0.5 * (Sk.x + Sn.x), 0.5 * (Sk.y - Sn.y));
+					const double2 d = make_double2(0.5 * (Sk.x - Sn.x), 0.5 * (Sk.y + Sn.y));
+					const double2 o = cmul(cconj(w2[i]), d);
+					buf[spad(k)] = make_double2(e.x - o.y, -(e.y + o.x));
+					buf[spad(n)] = make_double2(e.x + o.y, -(o.x - e.y));
+				}
+			}
+		}
+#undef L0_K
+#undef L0_N
 	}
 	__syncthreads();
 	fft_forward_smem<N>(buf, a.ptw, t);
@@ -902,7 +943,8 @@ __global__ void __launch_bounds__(MacBatchCfg<T>::THREADS, MacBatchCfg<T>::MINB)
 }
 
 constexpr int FIR_T_BATCH = 4;   // default depth of the near tier; DSP_B200_FIR_T=6|8 selects the other instantiations
-constexpr int FIR_T_FAR = 12;    // default depth of the far tier; DSP_B200_FIR_T2=0|8|12|16
+constexpr int FIR_T_FAR = 8;      // default depth of the far tier (DSP_B200_FIR_T2=0|8|12|16) ...
+constexpr int FIR_FAR_MIN_P = 48; // ... on levels of at least this many partitions
 
 static bool batch_depth_ok(int T) { return T == 4 || T == 6 || T == 8 || T == 12 || T == 16; }
 static int batch_threads_for(int T)
@@ -1521,7 +1563,9 @@ struct FirOp : Op {
 					if (!use_pipe && pf == 2) {
 						// far tier: partitions >= t_far + 2, T = t_far periods per launch; only when the level is long
 						// enough for it to pay (the near tier keeps partitions t_batch + 2 .. t_far + 1)
-						int t2 = FIR_T_FAR;
+						// (measured, DESIGN.md K2: at 32 partitions the second tier saves 8 % of the bytes and no time; at 64
+						// partitions -- 2048-frame blocks -- it is worth 10 %)
+						int t2 = (L.P >= FIR_FAR_MIN_P) ? FIR_T_FAR : 0;
 						if (const char *e = getenv("DSP_B200_FIR_T2")) t2 = atoi(e);
 						if (!batch_depth_ok(t2) || t2 <= t_batch || t2 % t_batch != 0 || L.P < 2 * t2 + pf) t2 = 0;
 						if (t2 > 0) {
@@ -1529,8 +1573,10 @@ struct FirOp : Op {
 							d_V2 = dev_alloc<double2>((size_t) 2 * t_far * n_sel * L.B);
 							if (!d_V2) return -1;
 						}
+						// one tier: staggered (every block period carries the same launches); two tiers: whole launches (the
+						// small per-class launches of the deep tier run at half the efficiency of a whole one)
 						const char *sg = getenv("DSP_B200_FIR_STAGGER");
-						stagger = !(sg && sg[0] == '0');
+						stagger = sg ? sg[0] != '0' : t_far == 0;
 						for (cudaEvent_t &e : ev_bs) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return -1);
 					}
 				}

@@ -41,10 +41,10 @@ def write_ir(tmp_path, h):
     return p
 
 
-# <path>_t<near depth>[_f<far depth>][_u]: _u = every tier for all channels every T-th block instead of one residue
-# class of channels per block; no _f = the default far tier (12)
-VARIANTS = ["pipe_t4", "legacy_t4", "legacy_t4_f0_u", "legacy_t4_f0", "legacy_t4_f8", "legacy_t4_f12_u", "legacy_t6_f12", "legacy_t6_f0_u",
-            "legacy_t8_f0_u", "legacy_t8_f0"]
+# <path>_t<near depth>[_f<far depth>][_u|_s]: _u = every tier for all channels every T-th block, _s = one residue class
+# of channels per block; defaults at 32 partitions: no far tier, staggered
+VARIANTS = ["pipe_t4", "legacy_t4", "legacy_t4_f0_u", "legacy_t4_f8_s", "legacy_t4_f8_u", "legacy_t4_f12_u", "legacy_t4_f12_s", "legacy_t6_f12_s",
+            "legacy_t6_f0_u", "legacy_t8_f0_u", "legacy_t8_f0_s"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -68,9 +68,8 @@ def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_
     parts = variant.split("_")
     pipe, t = parts[0], parts[1][1:]
     far = next((q[1:] for q in parts[2:] if q[0] == "f"), None)
-    unstaggered = "u" in parts[2:]
-    with env(DSP_B200_FIR_PIPE="1" if pipe == "pipe" else "0", DSP_B200_FIR_T=t, DSP_B200_FIR_T2=far,
-             DSP_B200_FIR_STAGGER="0" if unstaggered else None):
+    stag = "0" if "u" in parts[2:] else "1" if "s" in parts[2:] else None
+    with env(DSP_B200_FIR_PIPE="1" if pipe == "pipe" else "0", DSP_B200_FIR_T=t, DSP_B200_FIR_T2=far, DSP_B200_FIR_STAGGER=stag):
         ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
         plan = ch.describe()[0]
     assert plan["levels"] == [{"B": 4096, "P": 32}] and plan["t_batch"] == int(t), plan
@@ -78,7 +77,8 @@ def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_
     if pipe == "pipe":
         assert plan["pipe_pf"] == int(t) + 2 and plan["t_far"] == 0, plan
     else:
-        assert plan["t_far"] == (12 if far is None else int(far)) and plan["stagger"] == (0 if unstaggered else 1), plan
+        assert plan["t_far"] == (0 if far is None else int(far)), plan
+        assert plan["stagger"] == (int(stag) if stag is not None else (1 if plan["t_far"] == 0 else 0)), plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, nblk * F, F)])
     ch.close()
     assert got.shape == want.shape
@@ -121,8 +121,8 @@ def test_pipe_more_channels_than_sms(gpu_lib, taps, shared, pipe):
         assert np.array_equal(got[:, 0], got[:, 40]) and np.array_equal(got[:, 3], got[:, 203])
 
 
-@pytest.mark.parametrize("pipe,taps", [(1, 60000), (0, 60000), (0, 120000)])
-def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe, taps):
+@pytest.mark.parametrize("pipe,taps,far", [(1, 60000, None), (0, 60000, None), (0, 120000, 12), (0, 120000, 8)])
+def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe, taps, far):
     """The block kernel behind a scattered selector, writing into the compact buffer of fir's latency ring, with
     whole blocks and ragged calls alternating on the same state (general path <-> fused / pipeline kernel, batched V kept
     current by both).  120000 taps = 30 partitions: both tiers of the batched tail."""
@@ -135,10 +135,10 @@ def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe, taps):
         N = 22 * F + 333
         x = rng.standard_normal((N, C)) * 0.2
         want = restate.fir_stream(x, h, selector=sel, latency=lat)
-        with env(DSP_B200_FIR_PIPE=pipe):
+        with env(DSP_B200_FIR_PIPE=pipe, DSP_B200_FIR_T2=far, DSP_B200_FIR_STAGGER="1" if far == 12 else None):
             ch = gpu_lib.Chain(fs, C).add_fir(h, selector=sel, latency=lat, block_hint=F)
             plan = ch.describe()[0]
-        assert plan["pipe"] == pipe and plan["t_batch"] == 4 and plan["t_far"] == (12 if taps > 100000 else 0), plan
+        assert plan["pipe"] == pipe and plan["t_batch"] == 4 and plan["t_far"] == (far or 0), plan
         cuts = [0, F, 2 * F, 2 * F + 100, 3 * F, 4 * F, 5 * F, 6 * F, 7 * F, 7 * F + 1, 8 * F - 1, 8 * F, 9 * F, 10 * F, 11 * F, 12 * F,
                 12 * F + 2000, 14 * F, 15 * F, 16 * F, 17 * F, 18 * F, 19 * F, 20 * F, 21 * F, 22 * F, N]
         got = np.concatenate([ch.run(x[a:b]).copy() for a, b in zip(cuts[:-1], cuts[1:])])
@@ -153,11 +153,12 @@ def test_pipe_selector_latency_and_ragged_mix(gpu_lib, pipe, taps):
         ch.close()
 
 
-@pytest.mark.parametrize("taps,pipe,far", [(20000, 1, None), (70000, 1, None), (20000, 0, None), (70000, 0, None), (140000, 0, 16), (140000, 0, 8)])
+@pytest.mark.parametrize("taps,pipe,far", [(20000, 1, None), (70000, 1, None), (20000, 0, None), (70000, 0, None), (70000, 0, 12), (140000, 0, 16),
+                                           (140000, 0, None)])
 def test_2048_frame_partitions(gpu_lib, taps, pipe, far):
     """Blocks of 2048 frames (the CLI default): a single level of 2048-frame partitions -- 10, 35 and 69 of them --
-    through the fused kernel's two-CTA cluster form + MAC + two batch tiers (far tier of 12 by default, 16 and 8 on
-    request), and through the 2048-point instantiation of the pipeline kernel.  8 channels: two clusters."""
+    through the fused kernel's two-CTA cluster form + MAC + one or two batch tiers (far tier of 8 from 48 partitions
+    on, 12 and 16 on request), and through the 2048-point instantiation of the pipeline kernel.  8 channels: two clusters."""
     from oracle import restate
     fs, C, F = 48000, 8, 2048
     rng = np.random.default_rng(taps)
@@ -171,7 +172,9 @@ def test_2048_frame_partitions(gpu_lib, taps, pipe, far):
     assert plan["pipe"] == pipe and plan["levels"][0]["B"] == 2048 and len(plan["levels"]) == 1, plan
     if not pipe:
         P = plan["levels"][0]["P"]
-        assert plan["t_far"] == ((far or 12) if P >= 2 * (far or 12) + 2 else 0) and plan["stagger"] == (1 if P >= 11 else 0), plan
+        want_far = far if far else (8 if P >= 48 else 0)
+        assert plan["t_far"] == (want_far if P >= 2 * want_far + 2 else 0), plan
+        assert plan["stagger"] == (1 if P >= 11 and plan["t_far"] == 0 else 0), plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, N, F)])
     ch.close()
     assert rms(got - want) <= RMS_TOL, rms(got - want)
