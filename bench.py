@@ -305,10 +305,11 @@ def fir_bytes_model(plan, C, F, h):
         # n partitions streams n + T - 1 rows of X and n of H once for T block periods, writes T rows of V and -- the
         # near tier of two -- reads the far tier's T rows
         mac = 16.0 * (tb * (1 + h) + 2)
-        tf = int(plan.get("t_far", 0))
-        n_near = (tf + pf if tf else P) - (tb + pf)
+        tf, fe = int(plan.get("t_far", 0)), int(plan.get("far_e", 0))
+        n_near = (tf + pf + fe if tf else P) - (tb + pf)
+        n_far = P - (tf + pf + fe)
         batch = 16.0 * ((n_near + tb - 1) + n_near * h + tb + (tb if tf else 0)) / tb
-        far = 16.0 * ((P - pf - 1) + (P - pf - tf) * h + tf) / tf if tf else 0.0
+        far = 16.0 * ((n_far + tf - 1) + n_far * h + tf) / tf if tf else 0.0
     else:
         mac = 16.0 * ((P - pf) * (1 + h) + 1)
         batch = 0.0
@@ -332,12 +333,15 @@ def eq_coefs(dsp, fs, n):
     return np.array([dsp.biquad_design(13, fs, EQ_F[i], 1.4, EQ_G[i]) for i in range(n)])
 
 
-def measure_configs(dsp, torch, irs, peak, local_rank, dropin_steps):
+def measure_configs(dsp, torch, irs, peak, local_rank, dropin_steps, only=None):
     """Driver-run numbers for the other BASELINE configs (device-resident, 200 blocks each after 5 warm-ups) and for
     the drop-in call path.  Every entry: Msamples/s in, ms per block, and the roofline fraction of its bound."""
     out = {}
     stream = torch.cuda.current_stream().cuda_stream
     steps, warm = 200, 5
+
+    def want(name):
+        return not only or name in only
 
     def entry(name, chain, C, F, fs, bytes_per_sample, extra=None, out_frames=None, note=None):
         d_in = [torch.from_numpy(make_block(F, C, 500 + i)).cuda() for i in range(4)]
@@ -359,42 +363,50 @@ def measure_configs(dsp, torch, irs, peak, local_rank, dropin_steps):
 
     # C2: 10-stage eq cascade, 256 ch, 4096-frame blocks (K1: one read + one write of the block)
     C, F = 256, 4096
-    ch = dsp.Chain(FS, C, devices=[local_rank]).add_biquad(eq_coefs(dsp, FS, 10))
-    out["C2"] = entry("10 x eq cascade, 256 ch, 48 kHz, 4096-frame blocks", ch, C, F, FS, 16.0,
-                      note="K1 fused cascade; FP64-issue/latency-bound, HBM bound is 16 B/sample")
+    if want("C2"):
+        ch = dsp.Chain(FS, C, devices=[local_rank]).add_biquad(eq_coefs(dsp, FS, 10))
+        out["C2"] = entry("10 x eq cascade, 256 ch, 48 kHz, 4096-frame blocks", ch, C, F, FS, 16.0,
+                          note="K1 fused cascade; FP64-issue/latency-bound, HBM bound is 16 B/sample")
     # C3: fir_p 131072 taps, 64 channels
-    C = 64
-    ch = dsp.Chain(FS, C, devices=[local_rank]).add_fir(irs[:, :C], block_hint=F)
-    plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
-    bps, _ = fir_bytes_model(plan, C, F, 1)
-    out["C3"] = entry("fir_p 131072 taps x 64 ch, per-channel IR, 4096-frame blocks", ch, C, F, FS, bps, extra={"plan": plan})
+    if want("C3"):
+        C = 64
+        ch = dsp.Chain(FS, C, devices=[local_rank]).add_fir(irs[:, :C], block_hint=F)
+        plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
+        bps, _ = fir_bytes_model(plan, C, F, 1)
+        out["C3"] = entry("fir_p 131072 taps x 64 ch, per-channel IR, 4096-frame blocks", ch, C, F, FS, bps, extra={"plan": plan})
     # H at the CLI's default block (dsp.h:38)
-    C, F2 = 256, 2048
-    ch = dsp.Chain(FS, C, devices=[local_rank]).add_fir(irs[:, :C], block_hint=F2)
-    plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
-    bps, _ = fir_bytes_model(plan, C, F2, 1)
-    out["H_2048"] = entry("fir_p 131072 taps x 256 ch, per-channel IR, 2048-frame blocks (CLI default)", ch, C, F2, FS, bps, extra={"plan": plan})
+    if want("H_2048"):
+        C, F2 = 256, 2048
+        ch = dsp.Chain(FS, C, devices=[local_rank]).add_fir(irs[:, :C], block_hint=F2)
+        plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
+        bps, _ = fir_bytes_model(plan, C, F2, 1)
+        out["H_2048"] = entry("fir_p 131072 taps x 256 ch, per-channel IR, 2048-frame blocks (CLI default)", ch, C, F2, FS, bps, extra={"plan": plan})
     # C4: resample 44100 -> 48000, 1024 ch
-    C, fs4 = 1024, 44100
-    ch = dsp.Chain(fs4, C, devices=[local_rank]).add_resample(48000)
-    of = ch.max_out_frames(F)
-    rp = dsp.resample_params(fs4, 48000)
-    flop_per_in = 2.0 * rp["taps_per_phase"] * rp["n"] / rp["d"]
-    e = entry("resample 44100 -> 48000, 1024 ch, 4096-frame blocks", ch, C, F, fs4, 8.0 * (1 + rp["n"] / rp["d"]), out_frames=of)
-    e["fp64"] = {"flop_per_input_sample": flop_per_in, "achieved_tflops": flop_per_in * e["value"] * 1e6 / 1e12,
-                 "fp64_tflops_measured": 37.1, "fp64_peak_source": "scripts/micro/dmma_probe.cu on this pool's B200 (round 1)",
-                 "frac_of_fp64_peak": flop_per_in * e["value"] * 1e6 / 1e12 / 37.1}
-    e["note"] = "polyphase form as north_star words it: FP64-tensor-core (DMMA) bound, not HBM bound"
-    out["C4"] = e
+    fs4 = 44100
+    if want("C4"):
+        C = 1024
+        ch = dsp.Chain(fs4, C, devices=[local_rank]).add_resample(48000)
+        of = ch.max_out_frames(F)
+        rp = dsp.resample_params(fs4, 48000)
+        flop_per_in = 2.0 * rp["taps_per_phase"] * rp["n"] / rp["d"]
+        e = entry("resample 44100 -> 48000, 1024 ch, 4096-frame blocks", ch, C, F, fs4, 8.0 * (1 + rp["n"] / rp["d"]), out_frames=of)
+        e["fp64"] = {"flop_per_input_sample": flop_per_in, "achieved_tflops": flop_per_in * e["value"] * 1e6 / 1e12,
+                     "fp64_tflops_measured": 37.1, "fp64_peak_source": "scripts/micro/dmma_probe.cu on this pool's B200 (round 1)",
+                     "frac_of_fp64_peak": flop_per_in * e["value"] * 1e6 / 1e12 / 37.1}
+        e["note"] = "polyphase form as north_star words it: FP64-tensor-core (DMMA) bound, not HBM bound"
+        out["C4"] = e
     # C5 share: 8 eq + fir_p 65536 (shared IR) + resample, 256 ch at 44100
-    C = 256
-    h5 = make_ir(65536, 0)
-    ch = dsp.Chain(fs4, C, devices=[local_rank]).add_biquad(eq_coefs(dsp, fs4, 8)).add_fir(h5, block_hint=F).add_resample(48000)
-    plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
-    bps, _ = fir_bytes_model(plan, C, F, 0)
-    of = ch.max_out_frames(F)
-    out["C5_share"] = entry("8 x eq + fir_p 65536 taps (shared IR) + resample 44100 -> 48000, 256 ch (one GPU's share of config 5)", ch, C, F,
-                            fs4, 16.0 + bps + 8.0 * (1 + 160.0 / 147.0), out_frames=of, extra={"plan": plan})
+    if want("C5_share"):
+        C = 256
+        h5 = make_ir(65536, 0)
+        ch = dsp.Chain(fs4, C, devices=[local_rank]).add_biquad(eq_coefs(dsp, fs4, 8)).add_fir(h5, block_hint=F).add_resample(48000)
+        plan = [op for op in ch.describe() if op.get("op") == "fir"][0]
+        bps, _ = fir_bytes_model(plan, C, F, 0)
+        of = ch.max_out_frames(F)
+        out["C5_share"] = entry("8 x eq + fir_p 65536 taps (shared IR) + resample 44100 -> 48000, 256 ch (one GPU's share of config 5)", ch, C, F,
+                                fs4, 16.0 + bps + 8.0 * (1 + 160.0 / 147.0), out_frames=of, extra={"plan": plan})
+    if not want("dropin"):
+        return out
 
     # e2e_dropin: run_effects_chain() of the reference chain runtime with the shim's GPU effects (shim/frontend.c)
     try:
@@ -466,6 +478,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--only-configs", default="", help="comma list out of C2,C3,H_2048,C4,C5_share,dropin (measurements)")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel (serialised) timing pass")
     ap.add_argument("--e2e-slabs", type=int, default=4, help="channel slabs of the synchronous host call (copy-in / kernels / copy-out of the slabs overlap)")
     ap.add_argument("--e2e-pipe-slabs", type=int, default=0, help="channel slabs with blocks in flight (0: same as --e2e-slabs)")
@@ -664,7 +677,8 @@ def main():
     configs = None
     if rank == 0 and world == 1 and not a.no_configs:
         try:
-            configs = measure_configs(dsp_b200, torch, irs if not a.shared_ir else make_irs(a.taps, C), peak, local_rank, dropin_steps=100)
+            configs = measure_configs(dsp_b200, torch, irs if not a.shared_ir else make_irs(a.taps, C), peak, local_rank, dropin_steps=100,
+                                        only=[v for v in a.only_configs.split(",") if v] or None)
         except Exception as ex:
             configs = {"error": str(ex)[:300]}
 

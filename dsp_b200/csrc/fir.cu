@@ -1370,6 +1370,11 @@ struct FirOp : Op {
 	// value), and the staggered schedule -- every block launches the tiers for the channels of one residue class
 	// (s mod T == block mod T) instead of all channels every T-th block, so that every block period carries the same work
 	int t_far = 0;
+	// The far tier works one near-tier period ahead: launched after block q it covers the periods q+3+far_e .. (it takes
+	// partitions >= t_far + 2 + far_e), so that the near-tier launch that starts from its sums comes far_e blocks later.
+	// Without it a whole-launch far tier (183 us at 64 partitions) sits between a block and the third block after it:
+	// the step time then depends on how fast that one launch happens to run (measured: 60 or 103 us per 2048-frame block).
+	int far_e = 0;
 	double2 *d_V2 = nullptr;             // far tier: V spectra for 2 t_far block periods
 	bool stagger = false;
 	cudaEvent_t ev_bs[8] = {};           // after the tier launches of a block (ring), ev_bs_last: the latest one
@@ -1402,8 +1407,8 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"stagger\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
-		         t_batch, t_far, stagger ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"far_e\":%d,\"stagger\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
+		         t_batch, t_far, far_e, stagger ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
 		return buf;
 	}
 
@@ -1443,7 +1448,7 @@ struct FirOp : Op {
 		n_levels = 0;
 		dev_free(d_V); dev_free(d_V2); dev_free(d_Y_side); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp); dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi); dev_free(d_stats);
-		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; stagger = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
+		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; far_e = 0; stagger = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
 		d_Ybulk = nullptr; d_lo = d_hi = nullptr; d_stats = nullptr;
 		ltmp_cap = 0; tail_pf = 0; t_batch = 0; use_pipe = false; pipe_pf = 0; nb_max = 1;
 		urgent_pending = false; pre_valid = false; abs_pos = 0; planned = false;
@@ -1567,9 +1572,10 @@ struct FirOp : Op {
 						// partitions -- 2048-frame blocks -- it is worth 10 %)
 						int t2 = (L.P >= FIR_FAR_MIN_P) ? FIR_T_FAR : 0;
 						if (const char *e = getenv("DSP_B200_FIR_T2")) t2 = atoi(e);
-						if (!batch_depth_ok(t2) || t2 <= t_batch || t2 % t_batch != 0 || L.P < 2 * t2 + pf) t2 = 0;
+						if (!batch_depth_ok(t2) || t2 <= t_batch || t2 % t_batch != 0 || L.P < 2 * t2 + pf + t_batch) t2 = 0;
 						if (t2 > 0) {
 							t_far = t2;
+							far_e = t_batch;
 							d_V2 = dev_alloc<double2>((size_t) 2 * t_far * n_sel * L.B);
 							if (!d_V2) return -1;
 						}
@@ -1843,8 +1849,8 @@ struct FirOp : Op {
 			b.fdl = L.fdl; b.H = L.H; b.N = L.B; b.P = L.P; b.n_sel = n_sel; b.q = q;
 			b.V = i ? d_V2 : d_V; b.n_slots = 2 * T;
 			b.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
-			b.pf = 2;
-			b.p_lo = T + 2; b.p_hi = (i == 0 && t_far > 0) ? t_far + 2 : L.P;
+			b.pf = i ? 2 + far_e : 2;
+			b.p_lo = T + b.pf; b.p_hi = (i == 0 && t_far > 0) ? t_far + 2 + far_e : L.P;
 			if (i == 0 && t_far > 0) { b.Vin = d_V2; b.vin_slots = 2 * t_far; }
 			b.s_first = stagger ? g : 0; b.s_step = stagger ? T : 1;
 			int threads = batch_threads_for(T);

@@ -173,7 +173,7 @@ def test_2048_frame_partitions(gpu_lib, taps, pipe, far):
     if not pipe:
         P = plan["levels"][0]["P"]
         want_far = far if far else (8 if P >= 48 else 0)
-        assert plan["t_far"] == (want_far if P >= 2 * want_far + 2 else 0), plan
+        assert plan["t_far"] == (want_far if P >= 2 * want_far + 2 + 4 else 0), plan
         assert plan["stagger"] == (1 if P >= 11 and plan["t_far"] == 0 else 0), plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, N, F)])
     ch.close()
