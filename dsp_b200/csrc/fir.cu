@@ -1581,8 +1581,10 @@ struct FirOp : Op {
 						}
 						// one tier: staggered (every block period carries the same launches); two tiers: whole launches (the
 						// small per-class launches of the deep tier run at half the efficiency of a whole one)
+						// (and a tail too short for its per-class launches to be worth their overhead: config 5's 16
+						// partitions measured 180 us per block in whole launches, 195 staggered)
 						const char *sg = getenv("DSP_B200_FIR_STAGGER");
-						stagger = sg ? sg[0] != '0' : t_far == 0;
+						stagger = sg ? sg[0] != '0' : (t_far == 0 && L.P - t_batch - pf >= 16);
 						for (cudaEvent_t &e : ev_bs) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return -1);
 					}
 				}
