@@ -3,7 +3,7 @@
 (gpurun_out/prof_fir_step.ncu-rep, see scripts/gpu_round.sh): DRAM bytes (read + write) per launch of each
 kernel, times its launches per step as counted in the same capture window.
 
-    python scripts/traffic_from_ncu.py [C F taps h [far]]      # defaults: 256 4096 131072 1 12 (far: depth of the far batch tier)
+    python scripts/traffic_from_ncu.py [C F taps h [far [stagger]]]      # defaults: 256 4096 131072 1 12 1
 """
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,14 +22,24 @@ for r in rows[2:]:
     b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
     per.setdefault(name, []).append((b, float(r[ti])))
 pipe = any(k.startswith("k_fir_pipe") for k in per)
+stagger = int(sys.argv[6]) if len(sys.argv) >= 7 else 1
 n_l0 = sum(len(v) for k, v in per.items() if k.startswith("k_fir_pipe" if pipe else "k_fir_level0"))   # one block kernel launch per step
 out = {"kernels": {}, "window_steps": n_l0}
 total = 0.0
 for k, v in per.items():
     avg = sum(b for b, _ in v) / len(v)
-    out["kernels"][k] = {"dram_bytes_per_launch": avg, "launches_in_window": len(v), "launches_per_step": len(v) / max(n_l0, 1),
+    # launches per step by construction (the capture window cuts steps at both ends): the block kernel and the MAC
+    # once, a batch tier once when staggered (one channel class per block) and every T-th block otherwise; plan-time
+    # kernels (k_fir_fwd: the filter spectra) do not belong to a step
+    if k.startswith("k_fir_fwd") or k.startswith("k_fir_inv"):
+        lps = 0.0
+    elif k.startswith("k_fir_mac_batch") and not stagger:
+        lps = 1.0 / int(k.split("<")[1].split(",")[0])
+    else:
+        lps = 1.0
+    out["kernels"][k] = {"dram_bytes_per_launch": avg, "launches_in_window": len(v), "launches_per_step": lps,
                          "avg_us_under_ncu": sum(t for _, t in v) / len(v)}
-    total += avg * len(v) / max(n_l0, 1)
+    total += avg * lps
 out["dram_bytes_per_step"] = total
 out["source"] = "ncu --set full --clock-control none -k regex:k_fir_ (gpurun_out/prof_fir_step.ncu-rep); dram__bytes_read.sum + dram__bytes_write.sum"
 path = os.path.join(ROOT, "profiles", "traffic.json")
