@@ -374,6 +374,123 @@ __global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma(con
 	}
 }
 
+// The same kernel with the tap tile double-buffered: the gather of chunk k+1 (cp.async, 8 bytes each, straight into
+// the other half of S -- no registers, zero fill past the last row) is in flight while the DMMAs of chunk k run, one
+// barrier per chunk instead of a gather phase in which the CTA's four warps issue no DMMA at all (ncu, round 1:
+// tensor pipe busy 73 % of the time the SMs are active).  Chunks of 64 rows: the two halves together are the 40 KB of
+// the single-buffered form, four CTAs per SM as before.
+constexpr int RSM2_ROWS = 64;
+constexpr int RS_DEFAULT_MMA = 4;   // 4: single-buffered, 5: double-buffered tap tile
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
+{
+	const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+	const int nbytes = valid ? 8 : 0;   // 0: nothing is read, 8 zero bytes are written
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma2(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
+                                                        int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
+{
+	constexpr int MT = 4, NT = 4, Q = RSM_Q, LD = RSM_LD, ROWS = RSM2_ROWS;
+	__shared__ __align__(16) double S[2][ROWS * LD];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int g = lane >> 2, t = lane & 3;
+	const int c0w = (blockIdx.y * WARPS + warp) * 32;
+	const long q0 = (long) blockIdx.x * Q;
+	const long q_last = (q0 + Q - 1 < n_out) ? q0 + Q - 1 : n_out - 1;
+	const long i_top = ((m0 + q_last) * d) / n;
+	long i_bot = ((m0 + q0) * d) / n - in_len + 1;
+	if (i_bot < 0) i_bot = 0;   // rows before the stream start are zero
+	const int k_end = (int) (i_top - i_bot + 1);
+	double acc[MT][NT][2];
+#pragma unroll
+	for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+		for (int j = 0; j < NT; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+	// this lane fills columns g, g + 8, g + 16, g + 24 of S, rows k = 4 kg + t: tap of row i_top - k of the output
+	// frame's phase (the index may be <= 0: left pad of G's rows)
+	long goff[MT];
+#pragma unroll
+	for (int m = 0; m < MT; ++m) {
+		long q = q0 + g + 8 * m;
+		if (q >= n_out) q = n_out - 1;
+		const long md = (m0 + q) * d, ih = md / n;
+		goff[m] = (md - ih * n) * g_stride + pad + (ih - i_top);
+	}
+	auto gather = [&](int kk, double *Sb) {
+		for (int kg = warp; kg < ROWS / 4; kg += WARPS) {
+			const int k = 4 * kg + t;
+			const bool in = kk + k < k_end;
+#pragma unroll
+			for (int m = 0; m < MT; ++m) cp_async8(&Sb[k * LD + g + 8 * m], G + (in ? goff[m] + kk + k : 0), in);
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	gather(0, S[0]);
+	// B operand: 4 adjacent channels of row i_top - (4 step + t); lanes past the last channel read channel 0
+	const int cl = c0w + 4 * g;
+	const double *col = ring + ((cl < C) ? cl : 0);
+	long row = (i_top - t) % ring_len;
+	if (row < 0) row += ring_len;
+	double bn[NT];
+	{
+		const double *p = col + row * C;
+		const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+		bn[0] = u.x; bn[1] = u.y; bn[2] = v.x; bn[3] = v.y;
+		row -= 4;
+		if (row < 0) row += ring_len;
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	__syncthreads();
+	int cur = 0;
+	for (int kk = 0; kk < k_end; kk += ROWS) {
+		if (kk + ROWS < k_end) gather(kk + ROWS, S[cur ^ 1]);   // nobody reads that half any more (barrier below)
+		const double *Sc = S[cur];
+		const int left = k_end - kk;
+		const int steps = (left < ROWS) ? (left + 3) / 4 : ROWS / 4;
+		for (int st = 0; st < steps; ++st) {
+			double b[NT];
+#pragma unroll
+			for (int j = 0; j < NT; ++j) b[j] = bn[j];
+			{
+				const double *p = col + row * C;
+				const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+				bn[0] = u.x; bn[1] = u.y; bn[2] = v.x; bn[3] = v.y;
+				row -= 4;
+				if (row < 0) row += ring_len;
+			}
+			double a[MT];
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt) a[mt] = Sc[(4 * st + t) * LD + 8 * mt + g];
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+				for (int j = 0; j < NT; ++j) dmma884(acc[mt][j], a[mt], b[j]);
+		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads();   // the next half is complete and visible; this half is free
+		cur ^= 1;
+	}
+	// D fragment: row lane/4, columns 2 t and 2 t + 1 of n-tile j = channels c0w + 8 t + j and c0w + 8 t + 4 + j
+	const int ch = c0w + 8 * t;
+#pragma unroll
+	for (int mt = 0; mt < MT; ++mt) {
+		const long q = q0 + 8 * mt + g;
+		if (q >= n_out) continue;
+		double *o = out + q * C + ch;
+		if (ch < C) {
+			*reinterpret_cast<double2 *>(o) = make_double2(acc[mt][0][0], acc[mt][1][0]);
+			*reinterpret_cast<double2 *>(o + 2) = make_double2(acc[mt][2][0], acc[mt][3][0]);
+		}
+		if (ch + 4 < C) {
+			*reinterpret_cast<double2 *>(o + 4) = make_double2(acc[mt][0][1], acc[mt][1][1]);
+			*reinterpret_cast<double2 *>(o + 6) = make_double2(acc[mt][2][1], acc[mt][3][1]);
+		}
+	}
+}
+
 template <int R, int CH, int WARPS, int MINB>
 static void rs_launch(cudaStream_t st, const double *ring, long ring_len, int C, const double *G, int g_stride, int pad,
                       const ResampleParams &p, long m0, long n_out, double *out)
@@ -487,11 +604,20 @@ struct ResampleOp : Op {
 		const long first_m = emit_pos;   // emission is one contiguous raw range per call
 		if (oframes > 0) {
 			ProfScope prof("resample", st);
-			// DSP_B200_RS_TILE: 0 auto, 1..3 the FMA tiles (16x4, 16x2, 8x1), 4 tensor-core kernel
+			// DSP_B200_RS_TILE: 0 auto, 1..3 the FMA tiles (16x4, 16x2, 8x1), 4 tensor-core kernel, 5 the same with the
+			// tap tile double-buffered (cp.async)
 			static const int force = getenv("DSP_B200_RS_TILE") ? atoi(getenv("DSP_B200_RS_TILE")) : 0;
-			int tile = (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 3;
-			if (force >= 1 && force <= 4 && !(((force == 1 || force == 4) && C % 4) || (force == 2 && C % 2))) tile = force;
-			if (tile == 4) {
+			int tile = (C % 4 == 0) ? RS_DEFAULT_MMA : (C % 2 == 0) ? 2 : 3;
+			if (force >= 1 && force <= 5 && !(((force == 1 || force >= 4) && C % 4) || (force == 2 && C % 2))) tile = force;
+			if (tile == 5) {
+				const long tiles = ceil_div(oframes, RSM_Q);
+				const int w = (C >= 128 && tiles * ceil_div(C, 128) >= 148L * 3) ? 4 : (C >= 64 && tiles * ceil_div(C, 64) >= 148L * 2) ? 2 : 1;
+				const dim3 grid((unsigned) tiles, (unsigned) ceil_div(C, 32 * w));
+				if (w == 4) LAUNCH((k_rs_mma2<4>), grid, 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+				else if (w == 2) LAUNCH((k_rs_mma2<2>), grid, 64, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+				else LAUNCH((k_rs_mma2<1>), grid, 32, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+			}
+			else if (tile == 4) {
 				// 4 warps (128 channels) per CTA when that still gives every SM a few CTAs, else 2 or 1
 				const long tiles = ceil_div(oframes, RSM_Q);
 				const int w = (C >= 128 && tiles * ceil_div(C, 128) >= 148L * 3) ? 4 : (C >= 64 && tiles * ceil_div(C, 64) >= 148L * 2) ? 2 : 1;
