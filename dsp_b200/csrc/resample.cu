@@ -389,8 +389,10 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, 
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma2(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
+// DEPTH: steps the B rows (global loads of the input ring) are requested ahead of their use (ncu on the single-buffered
+// form: a quarter of the stall samples are long-scoreboard waits for them at one step ahead)
+template <int WARPS, int MINB, int DEPTH>
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_rs_mma2(const double *__restrict__ ring, long ring_len, int C, const double *__restrict__ G,
                                                         int g_stride, int pad, int n, int d, int in_len, long m0, long n_out, double *__restrict__ out)
 {
 	constexpr int MT = 4, NT = 4, Q = RSM_Q, LD = RSM_LD, ROWS = RSM2_ROWS;
@@ -434,11 +436,12 @@ __global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma2(co
 	const double *col = ring + ((cl < C) ? cl : 0);
 	long row = (i_top - t) % ring_len;
 	if (row < 0) row += ring_len;
-	double bn[NT];
-	{
+	double bq[DEPTH][NT];
+#pragma unroll
+	for (int dd = 0; dd < DEPTH; ++dd) {
 		const double *p = col + row * C;
 		const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
-		bn[0] = u.x; bn[1] = u.y; bn[2] = v.x; bn[3] = v.y;
+		bq[dd][0] = u.x; bq[dd][1] = u.y; bq[dd][2] = v.x; bq[dd][3] = v.y;
 		row -= 4;
 		if (row < 0) row += ring_len;
 	}
@@ -453,11 +456,15 @@ __global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma2(co
 		for (int st = 0; st < steps; ++st) {
 			double b[NT];
 #pragma unroll
-			for (int j = 0; j < NT; ++j) b[j] = bn[j];
+			for (int j = 0; j < NT; ++j) b[j] = bq[0][j];
+#pragma unroll
+			for (int dd = 0; dd + 1 < DEPTH; ++dd)
+#pragma unroll
+				for (int j = 0; j < NT; ++j) bq[dd][j] = bq[dd + 1][j];
 			{
 				const double *p = col + row * C;
 				const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
-				bn[0] = u.x; bn[1] = u.y; bn[2] = v.x; bn[3] = v.y;
+				bq[DEPTH - 1][0] = u.x; bq[DEPTH - 1][1] = u.y; bq[DEPTH - 1][2] = v.x; bq[DEPTH - 1][3] = v.y;
 				row -= 4;
 				if (row < 0) row += ring_len;
 			}
@@ -604,18 +611,22 @@ struct ResampleOp : Op {
 		const long first_m = emit_pos;   // emission is one contiguous raw range per call
 		if (oframes > 0) {
 			ProfScope prof("resample", st);
-			// DSP_B200_RS_TILE: 0 auto, 1..3 the FMA tiles (16x4, 16x2, 8x1), 4 tensor-core kernel, 5 the same with the
-			// tap tile double-buffered (cp.async)
+			// DSP_B200_RS_TILE: 0 auto, 1..3 the FMA tiles (16x4, 16x2, 8x1), 4 tensor-core kernel, 5..7 the same with the
+			// tap tile double-buffered (cp.async) and the input rows requested 2 / 3 / 2 steps ahead at 4 / 3 / 3 CTAs per SM
 			static const int force = getenv("DSP_B200_RS_TILE") ? atoi(getenv("DSP_B200_RS_TILE")) : 0;
 			int tile = (C % 4 == 0) ? RS_DEFAULT_MMA : (C % 2 == 0) ? 2 : 3;
-			if (force >= 1 && force <= 5 && !(((force == 1 || force >= 4) && C % 4) || (force == 2 && C % 2))) tile = force;
-			if (tile == 5) {
+			if (force >= 1 && force <= 7 && !(((force == 1 || force >= 4) && C % 4) || (force == 2 && C % 2))) tile = force;
+			if (tile >= 5) {
 				const long tiles = ceil_div(oframes, RSM_Q);
 				const int w = (C >= 128 && tiles * ceil_div(C, 128) >= 148L * 3) ? 4 : (C >= 64 && tiles * ceil_div(C, 64) >= 148L * 2) ? 2 : 1;
 				const dim3 grid((unsigned) tiles, (unsigned) ceil_div(C, 32 * w));
-				if (w == 4) LAUNCH((k_rs_mma2<4>), grid, 128, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
-				else if (w == 2) LAUNCH((k_rs_mma2<2>), grid, 64, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
-				else LAUNCH((k_rs_mma2<1>), grid, 32, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out);
+#define RS_MMA2(W, MINB, DEPTH) LAUNCH((k_rs_mma2<W, MINB, DEPTH>), grid, 32 * W, 0, st, d_ring, ring_len, C, d_G, g_stride, g_pad, p.n, p.d, p.in_len, first_m, oframes, out)
+				if (w == 4 && tile == 5) RS_MMA2(4, 4, 2);
+				else if (w == 4 && tile == 6) RS_MMA2(4, 3, 3);
+				else if (w == 4) RS_MMA2(4, 3, 2);
+				else if (w == 2) RS_MMA2(2, 1, 2);
+				else RS_MMA2(1, 1, 2);
+#undef RS_MMA2
 			}
 			else if (tile == 4) {
 				// 4 warps (128 channels) per CTA when that still gives every SM a few CTAs, else 2 or 1
