@@ -648,7 +648,7 @@ long dspb200_chain_submit_host(dspb200_chain *c, long frames, const double *in, 
 		bool rate_change = false;
 		for (auto &op : s->ops) rate_change |= !op->inplace_ok;
 		double *dst = rate_change ? s->buf[3] : s->buf[0];
-		const long f = s->run_ops(0, frames, s->buf[0], dst, true, s->stream);
+		const long f = s->run_ops(0, frames, s->buf[0], dst, true, s->stream, /* one block at a time: */ ticket == nullptr);
 		if (f < 0) return -1;
 		if (copy_slab(*s, C, f, dst, nullptr, out)) return -1;
 		if (ticket) {

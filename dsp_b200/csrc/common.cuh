@@ -91,7 +91,7 @@ struct Op {
 	int channels = 0;      // channels of this shard's slab
 	int fs_in = 0, fs_out = 0;
 	bool inplace_ok = true;   // run() accepts in == out
-	bool host_mode = false;   // set by the chain: the block came from / goes back to host memory in this call
+	bool host_mode = false;   // set by the chain: a synchronous host call (one block at a time, copied in and out within the call)
 	virtual ~Op() {}
 	virtual const char *name() const = 0;
 	virtual std::string describe() const { return std::string("{\"op\":\"") + name() + "\"}"; }

@@ -2108,8 +2108,8 @@ struct FirOp : Op {
 					f.P = (L0.P < 2) ? L0.P : 2; f.slot = (int) (L0.blk % L0.R);
 					f.out = d_ytmp; f.out_ch_stride = B0; f.carry = L0.carry; f.tw = L0.tw; f.ptw = L0.ptw; f.n_ch = n_sel;
 					cudaStream_t ls = st;
-					// (not for a block that came from host memory in this call: the synchronous host call works on one block
-					// at a time, the two event hops cost it 10 us per block and the priority buys it nothing)
+					// (not in a synchronous host call: it works on one block at a time, the two event hops cost it 10 us per
+					// block and the priority buys it nothing; with blocks in flight -- submit/wait -- it is worth 4 %)
 					const bool use_hot = hot && direct && tail_pf == 2 && !host_mode && !g_fir_serialize.load(std::memory_order_relaxed);
 					if (use_hot) {
 						CUDA_TRY(cudaEventRecord(ev_hot_in, st), return -1);

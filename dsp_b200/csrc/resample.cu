@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(32 * WARPS, (WARPS == 4) ? 4 : 1) k_rs_mma(con
 // tensor pipe busy 73 % of the time the SMs are active).  Chunks of 64 rows: the two halves together are the 40 KB of
 // the single-buffered form, four CTAs per SM as before.
 constexpr int RSM2_ROWS = 64;
-constexpr int RS_DEFAULT_MMA = 4;   // 4: single-buffered, 5: double-buffered tap tile
+constexpr int RS_DEFAULT_MMA = 7;   // 4: single-buffered tap tile; 7: double-buffered, input rows two steps ahead, 3 CTAs per SM (no spills)
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
 {
