@@ -316,6 +316,9 @@ def fir_bytes_model(plan, C, F, h):
     parts = {"stash_unstash": 0.0, "fir_level0": 0.0, "fir_fwd_inv": 0.0, "fir_mac": mac, "fir_mac_batch": batch}
     if pf and tb and int(plan.get("t_far", 0)):
         parts["fir_mac_batch_far"] = far
+    if int(plan.get("merge", 0)):
+        # the per-block MAC and the batch launch of the block are one grid
+        parts["fir_tail"] = parts.pop("fir_mac") + parts.pop("fir_mac_batch")
     direct = n_lv == 1 and (pf != 0 or P <= 2)
     if not direct:
         parts["stash_unstash"] = 16.0 + (8.0 + 8.0 * (n_lv - 1) + 8.0)
@@ -570,7 +573,7 @@ def main():
         pass
     step_s = ms / steps * 1e-3
     ach = per_sample * C * F / step_s / 1e9
-    knames = ("fir_pipe", "fir_level0", "fir_mac", "fir_mac_batch", "fir_mac_batch_far", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk")
+    knames = ("fir_pipe", "fir_level0", "fir_tail", "fir_mac", "fir_mac_batch", "fir_mac_batch_far", "fir_fwd", "fir_inv", "fir_mac_head", "fir_mac_bulk")
     roofline = {"bound": "hbm",
                 "kernel": "one step = every kernel of the chain for one block, the look-ahead MACs on their own streams",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

@@ -754,10 +754,10 @@ struct MacArgs {
 // that holds it compiles the special case (DCW); everywhere else the inner loop is the plain complex MAC, without
 // predicated-off copies of every FMA.
 template <bool SHARED_H, bool DCW>
-__device__ __forceinline__ void fir_mac_body(const MacArgs &a)
+__device__ __forceinline__ void fir_mac_body(const MacArgs &a, int y)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	const int s = blockIdx.y;
+	const int s = y;
 	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
 	double2 acc0 = a.init ? __ldcs(&a.init[(long) s * a.N + k]) : make_double2(0.0, 0.0);
@@ -808,8 +808,8 @@ __device__ __forceinline__ void fir_mac_body(const MacArgs &a)
 template <bool SHARED_H>
 __global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_mac(MacArgs a)
 {
-	if (blockIdx.x == 0 && threadIdx.x < 32) fir_mac_body<SHARED_H, true>(a);
-	else fir_mac_body<SHARED_H, false>(a);
+	if (blockIdx.x == 0 && threadIdx.x < 32) fir_mac_body<SHARED_H, true>(a, blockIdx.y);
+	else fir_mac_body<SHARED_H, false>(a, blockIdx.y);
 }
 
 // Time-batched tail of the last level.  With V_j = sum_{p in [p_lo, p_hi)} X_{j-p} H_p, p_lo >= pf+T (the part of
@@ -852,10 +852,10 @@ struct MacBatchCfg {
 };
 
 template <int T, bool SHARED_H, bool DCW>
-__device__ __forceinline__ void fir_mac_batch_body(const MacBatchArgs &a)
+__device__ __forceinline__ void fir_mac_batch_body(const MacBatchArgs &a, int y)
 {
 	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	const int s = a.s_first + blockIdx.y * a.s_step;
+	const int s = a.s_first + y * a.s_step;
 	const double2 *fdl = a.fdl + (long) s * a.P * a.N + k;
 	const double2 *H = a.H + (long) s * a.h_ch_stride + k;
 	const bool dc = DCW && (k == 0);
@@ -938,8 +938,33 @@ __device__ __forceinline__ void fir_mac_batch_body(const MacBatchArgs &a)
 template <int T, bool SHARED_H>
 __global__ void __launch_bounds__(MacBatchCfg<T>::THREADS, MacBatchCfg<T>::MINB) k_fir_mac_batch(MacBatchArgs a)
 {
-	if (blockIdx.x == 0 && threadIdx.x < 32) fir_mac_batch_body<T, SHARED_H, true>(a);   // the warp that holds the packed bin 0
-	else fir_mac_batch_body<T, SHARED_H, false>(a);
+	if (blockIdx.x == 0 && threadIdx.x < 32) fir_mac_batch_body<T, SHARED_H, true>(a, blockIdx.y);   // the warp that holds the packed bin 0
+	else fir_mac_batch_body<T, SHARED_H, false>(a, blockIdx.y);
+}
+
+// The per-block MAC and the staggered batch launch of the same block period in ONE grid: rows [0, n_batch_y) of the grid
+// are the batch tier's channels of this block's residue class (long CTAs first), the rest the per-block MAC of every
+// channel.  Neither depends on the other (both read blocks <= q and what earlier launches produced), and together
+// they fill the machine evenly: alone, a class launch of the batch tier is 2.3 waves of 15 us CTAs (0.73 of the HBM
+// peak) and the MAC a 27 us kernel with its own ramps.
+struct TailArgs {
+	MacArgs m;
+	MacBatchArgs b;
+	int n_batch_y;
+};
+
+template <int T, bool SHARED_H>
+__global__ void __launch_bounds__(256, FIR_MAC_MINB) k_fir_tail(TailArgs a)
+{
+	const bool dcw = blockIdx.x == 0 && threadIdx.x < 32;
+	if ((int) blockIdx.y < a.n_batch_y) {
+		if (dcw) fir_mac_batch_body<T, SHARED_H, true>(a.b, blockIdx.y);
+		else fir_mac_batch_body<T, SHARED_H, false>(a.b, blockIdx.y);
+	}
+	else {
+		if (dcw) fir_mac_body<SHARED_H, true>(a.m, (int) blockIdx.y - a.n_batch_y);
+		else fir_mac_body<SHARED_H, false>(a.m, (int) blockIdx.y - a.n_batch_y);
+	}
 }
 
 constexpr int FIR_T_BATCH = 4;   // default depth of the near tier; DSP_B200_FIR_T=6|8 selects the other instantiations
@@ -1375,6 +1400,7 @@ struct FirOp : Op {
 	// Without it a whole-launch far tier (183 us at 64 partitions) sits between a block and the third block after it:
 	// the step time then depends on how fast that one launch happens to run (measured: 60 or 103 us per 2048-frame block).
 	int far_e = 0;
+	bool merge_tail = false;             // the per-block MAC and the staggered batch launch as one grid (k_fir_tail)
 	double2 *d_V2 = nullptr;             // far tier: V spectra for 2 t_far block periods
 	bool stagger = false;
 	cudaEvent_t ev_bs[8] = {};           // after the tier launches of a block (ring), ev_bs_last: the latest one
@@ -1407,8 +1433,8 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"far_e\":%d,\"stagger\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
-		         t_batch, t_far, far_e, stagger ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"far_e\":%d,\"stagger\":%d,\"merge\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
+		         t_batch, t_far, far_e, stagger ? 1 : 0, merge_tail ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
 		return buf;
 	}
 
@@ -1448,7 +1474,7 @@ struct FirOp : Op {
 		n_levels = 0;
 		dev_free(d_V); dev_free(d_V2); dev_free(d_Y_side); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp); dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi); dev_free(d_stats);
-		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; far_e = 0; stagger = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
+		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; far_e = 0; stagger = false; merge_tail = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
 		d_Ybulk = nullptr; d_lo = d_hi = nullptr; d_stats = nullptr;
 		ltmp_cap = 0; tail_pf = 0; t_batch = 0; use_pipe = false; pipe_pf = 0; nb_max = 1;
 		urgent_pending = false; pre_valid = false; abs_pos = 0; planned = false;
@@ -1585,6 +1611,8 @@ struct FirOp : Op {
 						// partitions measured 180 us per block in whole launches, 195 staggered)
 						const char *sg = getenv("DSP_B200_FIR_STAGGER");
 						stagger = sg ? sg[0] != '0' : (t_far == 0 && L.P - t_batch - pf >= 16);
+						const char *mg = getenv("DSP_B200_FIR_MERGE");
+						merge_tail = stagger && t_far == 0 && t_batch == 4 && L.B >= 256 && !(mg && mg[0] == '0');
 						for (cudaEvent_t &e : ev_bs) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), return -1);
 					}
 				}
@@ -1819,6 +1847,31 @@ struct FirOp : Op {
 		if (!serial) {
 			CUDA_TRY(cudaEventRecord(ev_main, st), return -1);
 			if (!on_main) CUDA_TRY(cudaStreamWaitEvent(side, ev_main, 0), return -1);
+		}
+		if (merge_tail) {
+			// one grid for the per-block MAC (Y_{q+2}) and this block's class of the batch tier (V_{q+3} .. V_{q+6}); the
+			// MAC starts from V_{q+2}, which the launches up to block q-1 produced (same stream, in order)
+			TailArgs ta = {};
+			ta.m.fdl = L.fdl; ta.m.H = L.H; ta.m.Y = Y; ta.m.init = d_V + (size_t) (j % (2 * t_batch)) * n_sel * L.B;
+			ta.m.N = L.B; ta.m.P = L.R; ta.m.slot0 = (int) (j % L.R); ta.m.p0 = 2; ta.m.p1 = t_batch + 2;
+			ta.m.h_ch_stride = (fc == 1) ? 0 : (long) L.P * L.B;
+			const int g = (int) (q % t_batch);
+			ta.b.fdl = L.fdl; ta.b.H = L.H; ta.b.N = L.B; ta.b.P = L.P; ta.b.n_sel = n_sel; ta.b.q = q;
+			ta.b.V = d_V; ta.b.n_slots = 2 * t_batch; ta.b.h_ch_stride = ta.m.h_ch_stride;
+			ta.b.pf = 2; ta.b.p_lo = t_batch + 2; ta.b.p_hi = L.P;
+			ta.b.s_first = g; ta.b.s_step = t_batch;
+			ta.n_batch_y = (n_sel > g) ? (n_sel - g + t_batch - 1) / t_batch : 0;
+			const dim3 grid(L.B / 256, ta.n_batch_y + n_sel);
+			{
+				ProfScope prof("fir_tail", ts);
+				if (fc == 1) LAUNCH((k_fir_tail<4, true>), grid, 256, 0, ts, ta);
+				else LAUNCH((k_fir_tail<4, false>), grid, 256, 0, ts, ta);
+			}
+			CUDA_TRY(cudaEventRecord(ev_tail[j & 1], ts), return -1);
+			cudaEvent_t e = ev_bs[ev_bs_n++ & 7];   // the general path waits for the batch part through this one
+			CUDA_TRY(cudaEventRecord(e, ts), return -1);
+			ev_bs_last = e;
+			return 0;
 		}
 		if (t_batch > 0) {
 			// V_j is complete once every tier launch up to block q-1 is (one stream, in order)
