@@ -308,7 +308,7 @@ __device__ __forceinline__ void prefetch_rows(const void *p, long bytes, int t, 
 // (cp.async.bulk.shared::cluster.shared::cta), instead of plain distributed-shared-memory stores fenced by
 // cluster.sync().  The releasing cluster barrier compiles to MEMBAR.ALL.GPU (+ ERRBAR): every thread waits for all its
 // global stores and prefetches in flight, four times per block; a third of the kernel's stall samples were that wait
-// (profiles/r02_prof_fir_step_*).  Here nobody fences: a CTA de-interleaves its rows into a staging area, one thread
+// (profiles/r02a_prof_fir_step_*).  Here nobody fences: a CTA de-interleaves its rows into a staging area, one thread
 // sends each channel's chunk (8.5 KB, already in the padded layout of the transform buffer) to its owner, and a CTA
 // waits on its own mbarrier until the bytes addressed to it have landed.  (Per-element st.async -- 16 bytes and one
 // transaction-count update on the receiver's mbarrier each -- measured slower than the fenced form: 52 against
@@ -978,23 +978,36 @@ static int batch_threads_for(int T)
 	     : (T == 6) ? MacBatchCfg<6>::THREADS : MacBatchCfg<4>::THREADS;
 }
 
+// `smem`: dynamic shared memory the kernel does not use -- a cap on its CTAs per SM (a whole-launch far tier otherwise
+// fills every SM's registers with CTAs that live 20 us, and the next block's fused kernel waits for them to retire)
 template <int T>
-static void launch_mac_batch_t(bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b)
+static void launch_mac_batch_t(bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b, size_t smem)
 {
-	if (shared_h) LAUNCH((k_fir_mac_batch<T, true>), grid, threads, 0, st, b);
-	else LAUNCH((k_fir_mac_batch<T, false>), grid, threads, 0, st, b);
+	if (smem > 48 * 1024) {
+		static std::atomic<size_t> set[64];
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (set[dev & 63].load() < smem) {
+			cudaFuncSetAttribute((k_fir_mac_batch<T, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+			cudaFuncSetAttribute((k_fir_mac_batch<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+			set[dev & 63].store(smem);
+		}
+	}
+	if (shared_h) LAUNCH((k_fir_mac_batch<T, true>), grid, threads, smem, st, b);
+	else LAUNCH((k_fir_mac_batch<T, false>), grid, threads, smem, st, b);
 }
 
 // grid: x = N / threads, y = channels of this launch; `threads` at most batch_threads_for(T)
-static void launch_mac_batch(int T, bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b, const char *prof_name = "fir_mac_batch")
+static void launch_mac_batch(int T, bool shared_h, dim3 grid, int threads, cudaStream_t st, const MacBatchArgs &b, const char *prof_name = "fir_mac_batch",
+                             size_t smem = 0)
 {
 	ProfScope prof(prof_name, st);
 	switch (T) {
-	case 16: launch_mac_batch_t<16>(shared_h, grid, threads, st, b); break;
-	case 12: launch_mac_batch_t<12>(shared_h, grid, threads, st, b); break;
-	case 8: launch_mac_batch_t<8>(shared_h, grid, threads, st, b); break;
-	case 6: launch_mac_batch_t<6>(shared_h, grid, threads, st, b); break;
-	default: launch_mac_batch_t<4>(shared_h, grid, threads, st, b); break;
+	case 16: launch_mac_batch_t<16>(shared_h, grid, threads, st, b, smem); break;
+	case 12: launch_mac_batch_t<12>(shared_h, grid, threads, st, b, smem); break;
+	case 8: launch_mac_batch_t<8>(shared_h, grid, threads, st, b, smem); break;
+	case 6: launch_mac_batch_t<6>(shared_h, grid, threads, st, b, smem); break;
+	default: launch_mac_batch_t<4>(shared_h, grid, threads, st, b, smem); break;
 	}
 }
 
@@ -1915,7 +1928,10 @@ struct FirOp : Op {
 			if ((batch_threads == 128 || batch_threads == 64) && batch_threads < threads) threads = batch_threads;
 			if (L.B < threads) threads = L.B;
 			dim3 grid(L.B / threads, stagger ? (n_sel - g + T - 1) / T : n_sel);
-			launch_mac_batch(T, fc == 1, grid, threads, bs, b, i ? "fir_mac_batch_far" : "fir_mac_batch");
+			// whole launches of the far tier: at most one CTA per SM (DSP_B200_FIR_FAR_SMEM_KB, 0 = no cap)
+			static const long far_kb = getenv("DSP_B200_FIR_FAR_SMEM_KB") ? atol(getenv("DSP_B200_FIR_FAR_SMEM_KB")) : 0;
+			launch_mac_batch(T, fc == 1, grid, threads, bs, b, i ? "fir_mac_batch_far" : "fir_mac_batch",
+			                 (i && !stagger && far_kb > 0) ? (size_t) far_kb * 1024 : 0);
 		}
 		if (any) {
 			cudaEvent_t e = ev_bs[ev_bs_n++ & 7];
