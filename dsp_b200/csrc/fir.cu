@@ -1564,7 +1564,10 @@ struct FirOp : Op {
 				// stream waits for at its next block -- they must not queue behind the batched MAC's CTAs (measured: the
 				// same 2048-frame-block run took 68 or 350 us per block depending on who got the SMs first).  Single-level
 				// plans only keep look-ahead MACs there: lowest priority.
-				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, (n_levels > 1) ? hi : lo), return -1);
+				// (DSP_B200_FIR_MAC_PRIO: measurement -- the per-block MAC between the fused kernel and the batch tiers)
+				int side_prio = (n_levels > 1) ? hi : lo;
+				if (const char *e = getenv("DSP_B200_FIR_MAC_PRIO")) side_prio = (atoi(e) < hi) ? hi : (atoi(e) > lo) ? lo : atoi(e);
+				CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, side_prio), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_urgent, cudaEventDisableTiming), return -1);
 				CUDA_TRY(cudaEventCreateWithFlags(&ev_tail[0], cudaEventDisableTiming), return -1);
