@@ -619,7 +619,7 @@ def main():
                 # bytes_per_sample_by_kernel is per input sample; a launch of the batch kernel covers t_batch block periods
                 # (staggered: a launch covers 1/T of the channels for T periods = one block period's share)
                 depth = {"fir_mac_batch": plan.get("t_batch", 1), "fir_mac_batch_far": plan.get("t_far", 1)}.get(nme, 1)
-                mult = 1 if plan.get("stagger") else depth
+                mult = 1 if plan.get("stagger") else depth / max(1, plan.get("far_classes", 1)) if nme == "fir_mac_batch_far" else depth
                 e["algorithmic_bytes_per_launch"] = per_launch * nB * mult
                 e["alone_GBs"] = e["algorithmic_bytes_per_launch"] / (e["alone_us"] * 1e-6) / 1e9
                 e["alone_frac"] = e["alone_GBs"] / peak

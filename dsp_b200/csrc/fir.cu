@@ -1413,6 +1413,10 @@ struct FirOp : Op {
 	// Without it a whole-launch far tier (183 us at 64 partitions) sits between a block and the third block after it:
 	// the step time then depends on how fast that one launch happens to run (measured: 60 or 103 us per 2048-frame block).
 	int far_e = 0;
+	// Far tier in whole launches: far_classes residue classes of channels take turns, one launch every t_far /
+	// far_classes blocks (2: half the channels every fourth block at t_far = 8 -- the same work in every group of four
+	// blocks, and a launch half as long inside the same four blocks of lead)
+	int far_classes = 1;
 	bool merge_tail = false;             // the per-block MAC and the staggered batch launch as one grid (k_fir_tail)
 	double2 *d_V2 = nullptr;             // far tier: V spectra for 2 t_far block periods
 	bool stagger = false;
@@ -1446,8 +1450,8 @@ struct FirOp : Op {
 		                 filter_frames, n_sel, fc, latency, planned ? 1 : 0);
 		for (int l = 0; l < n_levels && n < (int) sizeof(buf) - 64; ++l)
 			n += snprintf(buf + n, sizeof(buf) - n, "%s{\"B\":%d,\"P\":%d}", l ? "," : "", lv[l].B, lv[l].P);
-		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"far_e\":%d,\"stagger\":%d,\"merge\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
-		         t_batch, t_far, far_e, stagger ? 1 : 0, merge_tail ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
+		snprintf(buf + n, sizeof(buf) - n, "],\"t_batch\":%d,\"t_far\":%d,\"far_e\":%d,\"far_classes\":%d,\"stagger\":%d,\"merge\":%d,\"tail_pf\":%d,\"bulk\":%d,\"pipe\":%d,\"pipe_pf\":%d}",
+		         t_batch, t_far, far_e, far_classes, stagger ? 1 : 0, merge_tail ? 1 : 0, tail_pf, nb_max, use_pipe ? 1 : 0, pipe_pf);
 		return buf;
 	}
 
@@ -1487,7 +1491,7 @@ struct FirOp : Op {
 		n_levels = 0;
 		dev_free(d_V); dev_free(d_V2); dev_free(d_Y_side); dev_free(d_hist); dev_free(d_ytmp); dev_free(d_pre); dev_free(d_h0);
 		dev_free(d_Y); dev_free(d_ring); dev_free(d_ltmp); dev_free(d_Ybulk); dev_free(d_lo); dev_free(d_hi); dev_free(d_stats);
-		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; far_e = 0; stagger = false; merge_tail = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
+		d_V = d_V2 = d_Y_side = nullptr; t_far = 0; far_e = 0; far_classes = 1; stagger = false; merge_tail = false; d_hist = d_ytmp = d_pre = d_h0 = nullptr; d_Y = nullptr; d_ring = d_ltmp = nullptr;
 		d_Ybulk = nullptr; d_lo = d_hi = nullptr; d_stats = nullptr;
 		ltmp_cap = 0; tail_pf = 0; t_batch = 0; use_pipe = false; pipe_pf = 0; nb_max = 1;
 		urgent_pending = false; pre_valid = false; abs_pos = 0; planned = false;
@@ -1627,6 +1631,12 @@ struct FirOp : Op {
 						// partitions measured 180 us per block in whole launches, 195 staggered)
 						const char *sg = getenv("DSP_B200_FIR_STAGGER");
 						stagger = sg ? sg[0] != '0' : (t_far == 0 && L.P - t_batch - pf >= 16);
+						if (t_far > 0 && !stagger) {
+							// the turns must start on near-tier launches: t_far / far_classes a multiple of t_batch
+							int fcls = 2;
+							if (const char *e = getenv("DSP_B200_FIR_FAR_CLASSES")) fcls = atoi(e);
+							far_classes = (fcls >= 1 && t_far % fcls == 0 && (t_far / fcls) % t_batch == 0) ? fcls : 1;
+						}
 						const char *mg = getenv("DSP_B200_FIR_MERGE");
 						// (opt-in: alone the one grid runs at 0.95 of the HBM peak -- 66 us against 27 + 52 --, but the fused
 						// kernel of the block after next then waits for all of it instead of the MAC part: 97 us per step
@@ -1914,9 +1924,13 @@ struct FirOp : Op {
 		bool any = false;
 		for (int i = (t_far > 0) ? 1 : 0; i >= 0; --i) {
 			const int T = i ? t_far : t_batch;
-			const int g = (int) (q % T);
-			if (!stagger && g != 0) continue;
-			if (stagger && n_sel <= g) continue;
+			// K residue classes of channels take turns, one launch every T / K blocks: K = T when staggered, 1 for whole
+			// launches, far_classes for the far tier in between
+			const int K = stagger ? T : (i ? far_classes : 1);
+			const int period = T / K;
+			if (q % period != 0) continue;
+			const int g = (int) ((q / period) % K);
+			if (n_sel <= g) continue;
 			if (!any && !serial) CUDA_TRY(cudaStreamWaitEvent(bs, ev_main, 0), return -1);
 			any = true;
 			MacBatchArgs b = {};
@@ -1926,11 +1940,11 @@ struct FirOp : Op {
 			b.pf = i ? 2 + far_e : 2;
 			b.p_lo = T + b.pf; b.p_hi = (i == 0 && t_far > 0) ? t_far + 2 + far_e : L.P;
 			if (i == 0 && t_far > 0) { b.Vin = d_V2; b.vin_slots = 2 * t_far; }
-			b.s_first = stagger ? g : 0; b.s_step = stagger ? T : 1;
+			b.s_first = g; b.s_step = K;
 			int threads = batch_threads_for(T);
 			if ((batch_threads == 128 || batch_threads == 64) && batch_threads < threads) threads = batch_threads;
 			if (L.B < threads) threads = L.B;
-			dim3 grid(L.B / threads, stagger ? (n_sel - g + T - 1) / T : n_sel);
+			dim3 grid(L.B / threads, (n_sel - g + K - 1) / K);
 			// whole launches of the far tier: at most one CTA per SM (DSP_B200_FIR_FAR_SMEM_KB, 0 = no cap)
 			static const long far_kb = getenv("DSP_B200_FIR_FAR_SMEM_KB") ? atol(getenv("DSP_B200_FIR_FAR_SMEM_KB")) : 0;
 			launch_mac_batch(T, fc == 1, grid, threads, bs, b, i ? "fir_mac_batch_far" : "fir_mac_batch",
