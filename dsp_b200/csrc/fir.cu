@@ -1414,8 +1414,7 @@ struct FirOp : Op {
 	// the step time then depends on how fast that one launch happens to run (measured: 60 or 103 us per 2048-frame block).
 	int far_e = 0;
 	// Far tier in whole launches: far_classes residue classes of channels take turns, one launch every t_far /
-	// far_classes blocks (2: half the channels every fourth block at t_far = 8 -- the same work in every group of four
-	// blocks, and a launch half as long inside the same four blocks of lead)
+	// far_classes blocks (DSP_B200_FIR_FAR_CLASSES=2: half the channels every fourth block at t_far = 8)
 	int far_classes = 1;
 	bool merge_tail = false;             // the per-block MAC and the staggered batch launch as one grid (k_fir_tail)
 	double2 *d_V2 = nullptr;             // far tier: V spectra for 2 t_far block periods
@@ -1633,7 +1632,8 @@ struct FirOp : Op {
 						stagger = sg ? sg[0] != '0' : (t_far == 0 && L.P - t_batch - pf >= 16);
 						if (t_far > 0 && !stagger) {
 							// the turns must start on near-tier launches: t_far / far_classes a multiple of t_batch
-							int fcls = 2;
+							// (measured on 2048-frame blocks, four runs each: two turns 63-73 us per block, one 61-67: one)
+							int fcls = 1;
 							if (const char *e = getenv("DSP_B200_FIR_FAR_CLASSES")) fcls = atoi(e);
 							far_classes = (fcls >= 1 && t_far % fcls == 0 && (t_far / fcls) % t_batch == 0) ? fcls : 1;
 						}

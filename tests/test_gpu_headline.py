@@ -42,9 +42,9 @@ def write_ir(tmp_path, h):
 
 
 # <path>_t<near depth>[_f<far depth>][_u|_s]: _u = every tier for all channels every T-th block, _s = one residue class
-# of channels per block (_u1: the far tier too; _u alone: the far tier in two turns), _m = the per-block MAC and the batch class as one grid; defaults at 32 partitions: no far tier,
+# of channels per block (_u2: the far tier in two turns, half the channels each), _m = the per-block MAC and the batch class as one grid; defaults at 32 partitions: no far tier,
 # staggered, two launches
-VARIANTS = ["pipe_t4", "legacy_t4", "legacy_t4_m", "legacy_t4_f0_u", "legacy_t4_f8_s", "legacy_t4_f8_u", "legacy_t4_f8_u1", "legacy_t4_f12_u", "legacy_t4_f12_s", "legacy_t6_f12_s",
+VARIANTS = ["pipe_t4", "legacy_t4", "legacy_t4_m", "legacy_t4_f0_u", "legacy_t4_f8_s", "legacy_t4_f8_u", "legacy_t4_f8_u2", "legacy_t4_f12_u", "legacy_t4_f12_s", "legacy_t6_f12_s",
             "legacy_t6_f0_u", "legacy_t8_f0_u", "legacy_t8_f0_s"]
 
 
@@ -69,9 +69,9 @@ def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_
     parts = variant.split("_")
     pipe, t = parts[0], parts[1][1:]
     far = next((q[1:] for q in parts[2:] if q[0] == "f"), None)
-    stag = "0" if ("u" in parts[2:] or "u1" in parts[2:]) else "1" if "s" in parts[2:] else None
+    stag = "0" if ("u" in parts[2:] or "u2" in parts[2:]) else "1" if "s" in parts[2:] else None
     with env(DSP_B200_FIR_PIPE="1" if pipe == "pipe" else "0", DSP_B200_FIR_T=t, DSP_B200_FIR_T2=far, DSP_B200_FIR_STAGGER=stag,
-             DSP_B200_FIR_MERGE="1" if "m" in parts[2:] else None, DSP_B200_FIR_FAR_CLASSES="1" if "u1" in parts[2:] else None):
+             DSP_B200_FIR_MERGE="1" if "m" in parts[2:] else None, DSP_B200_FIR_FAR_CLASSES="2" if "u2" in parts[2:] else None):
         ch = gpu_lib.Chain(fs, C).add_fir(h, block_hint=F)
         plan = ch.describe()[0]
     assert plan["levels"] == [{"B": 4096, "P": 32}] and plan["t_batch"] == int(t), plan
@@ -83,9 +83,8 @@ def test_headline_composition_against_compiled_reference(gpu_lib, have_ref, tmp_
         assert plan["stagger"] == (int(stag) if stag is not None else (1 if plan["t_far"] == 0 else 0)), plan
         assert plan["merge"] == (1 if "m" in parts[2:] else 0), plan
         if plan["t_far"] and not plan["stagger"]:
-            # whole launches of the far tier: halves of the channels in turns unless asked otherwise (12 / 2 = 6 is no
-            # multiple of the near depth 4: one class)
-            assert plan["far_classes"] == (1 if "u1" in parts[2:] or plan["t_far"] == 12 else 2), plan
+            # whole launches of the far tier for all channels, or on request for halves of them in turns
+            assert plan["far_classes"] == (2 if "u2" in parts[2:] else 1), plan
     got = np.concatenate([ch.run(x[i:i + F]).copy() for i in range(0, nblk * F, F)])
     ch.close()
     assert got.shape == want.shape
