@@ -13,6 +13,8 @@
 #include "../../include/dsp_b200.h"
 #include <cmath>
 #include <map>
+#include <mutex>
+#include <vector>
 
 namespace dspb200 {
 
@@ -21,6 +23,92 @@ namespace dspb200 {
 // ------------------------------------------------------------------------------------------
 static thread_local char tls_error[512] = "";
 std::atomic<long long> g_kernel_launches{0};
+
+// ---- cache of freed device blocks (common.cuh: dev_alloc / dev_free) ----------------------------
+namespace {
+struct PoolState {
+	std::mutex mu;
+	std::map<void *, std::pair<int, size_t>> live;                 // block -> (device, bytes)
+	std::multimap<std::pair<int, size_t>, void *> idle;            // (device, bytes) -> block
+	size_t idle_bytes = 0;
+	size_t cap = ((getenv("DSP_B200_POOL_MB") ? (size_t) atol(getenv("DSP_B200_POOL_MB")) : 8192)) << 20;
+};
+PoolState &pool()
+{
+	static PoolState *p = new PoolState();   // never destroyed: blocks may be freed from static destructors
+	return *p;
+}
+}   // namespace
+
+void *pool_alloc(size_t bytes)
+{
+	PoolState &ps = pool();
+	int dev = 0;
+	cudaGetDevice(&dev);
+	{
+		std::lock_guard<std::mutex> lk(ps.mu);
+		auto it = ps.idle.find(std::make_pair(dev, bytes));
+		if (it != ps.idle.end()) {
+			void *p = it->second;
+			ps.idle.erase(it);
+			ps.idle_bytes -= bytes;
+			ps.live[p] = std::make_pair(dev, bytes);
+			return p;
+		}
+	}
+	void *p = nullptr;
+	cudaError_t err = cudaMalloc(&p, bytes);
+	if (err != cudaSuccess) {
+		// give the cache back to the driver and try once more
+		std::vector<void *> drop;
+		{
+			std::lock_guard<std::mutex> lk(ps.mu);
+			for (auto &kv : ps.idle) drop.push_back(kv.second);
+			ps.idle.clear();
+			ps.idle_bytes = 0;
+		}
+		cudaGetLastError();
+		for (void *q : drop) cudaFree(q);
+		err = cudaMalloc(&p, bytes);
+	}
+	if (err != cudaSuccess) {
+		set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(err));
+		cudaGetLastError();
+		return nullptr;
+	}
+	std::lock_guard<std::mutex> lk(ps.mu);
+	ps.live[p] = std::make_pair(dev, bytes);
+	return p;
+}
+
+void pool_free(void *p)
+{
+	PoolState &ps = pool();
+	std::pair<int, size_t> info(0, 0);
+	bool keep = false;
+	{
+		std::lock_guard<std::mutex> lk(ps.mu);
+		auto it = ps.live.find(p);
+		if (it != ps.live.end()) {
+			info = it->second;
+			ps.live.erase(it);
+			keep = info.second >= (1u << 20) && ps.idle_bytes + info.second <= ps.cap;
+		}
+	}
+	if (!keep) {
+		cudaFree(p);
+		return;
+	}
+	// cudaFree would have waited for the device: whatever still uses the block must be done before it is handed out again
+	int cur = 0;
+	cudaGetDevice(&cur);
+	if (cur != info.first) cudaSetDevice(info.first);
+	cudaDeviceSynchronize();
+	if (cur != info.first) cudaSetDevice(cur);
+	std::lock_guard<std::mutex> lk(ps.mu);
+	ps.idle.insert(std::make_pair(info, p));
+	ps.idle_bytes += info.second;
+}
 std::atomic<long long> g_h2d_copies{0}, g_d2h_copies{0};   // host<->device block copies issued (dspb200_copy_counts)
 
 void set_error(const char *fmt, ...)
